@@ -1,0 +1,746 @@
+// C ABI of the library (include/bsde_b200.h): context, workspaces, and the host-side sequencing of the kernels.
+// The only host work per fit is enqueueing launches (one CUDA graph per ALS sweep); all arithmetic runs on the GPU.
+#include "../../include/bsde_b200.h"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace bsde {
+
+static thread_local std::string g_err;
+
+int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    cudaGetLastError();
+    return 1;
+}
+
+int fail_msg(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+// ---- NCCL, bound at run time so that the library loads (and single-GPU runs work) without it --------------
+typedef struct ncclComm* ncclComm_t;
+struct ncclUniqueId_ { char internal[128]; };
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId_*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail_msg(3, "NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+#define BSDE_SYM(field, name)                                                        \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, name);                               \
+    if (!g_nccl.field) return fail_msg(3, "NCCL symbol %s missing", name)
+    BSDE_SYM(GetUniqueId, "ncclGetUniqueId");
+    BSDE_SYM(CommInitRank, "ncclCommInitRank");
+    BSDE_SYM(AllReduce, "ncclAllReduce");
+    BSDE_SYM(CommDestroy, "ncclCommDestroy");
+    BSDE_SYM(GetErrorString, "ncclGetErrorString");
+#undef BSDE_SYM
+    return 0;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail_cuda(e, "cudaMalloc(workspace)", __FILE__, __LINE__); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+}  // namespace bsde
+
+using namespace bsde;
+
+struct bsde_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own = nullptr, stream = nullptr;
+    int64_t launches = 0;
+    int64_t use_graph = 1;
+    DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg;
+    std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+namespace {
+
+struct Guard {   // select the context's device for the duration of a call
+    int prev = -1;
+    explicit Guard(const bsde_ctx* c) { cudaGetDevice(&prev); if (prev != c->device) cudaSetDevice(c->device); else prev = -1; }
+    ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define BSDE_TRY(expr)            \
+    do {                          \
+        const int _rc = (expr);   \
+        if (_rc) return _rc;      \
+    } while (0)
+
+#define BSDE_CHECK_CTX(c) \
+    if (!(c)) return fail_msg(2, "null context")
+
+int get_plan(bsde_ctx* c, int rl, int p, int rr, int mono, int64_t N, const AsmPlan** out) {
+    auto key = std::make_tuple(rl, p, rr, mono, N);
+    auto it = c->plans.find(key);
+    if (it == c->plans.end()) {
+        if (c->plans.size() > 64) {
+            for (auto& kv : c->plans) asm_plan_free(kv.second);
+            c->plans.clear();
+        }
+        AsmPlan P;
+        BSDE_TRY(asm_plan_build(P, rl, p, rr, mono, N, c->sm_count));
+        it = c->plans.emplace(key, std::move(P)).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+// One tensor train on the device: cores at fixed slots of `slot` doubles (capacity for rank growth).
+struct Train {
+    int d = 0, p = 0;
+    std::vector<int> ranks;        // d+1
+    std::vector<int> cap;          // d+1 capacity ranks (>= ranks)
+    std::vector<int64_t> off;      // d offsets (doubles) into `cores`
+    double* cores = nullptr;       // device
+    int64_t* off_dev = nullptr;
+    int* ranks_dev = nullptr;
+    int64_t total = 0;
+    int max_rank() const { int m = 1; for (int r : ranks) m = r > m ? r : m; return m; }
+    double* core(int j) const { return cores + off[j]; }
+    int64_t size(int j) const { return (int64_t)ranks[j] * p * ranks[j + 1]; }
+};
+
+int check_ranks(int d, int p, const int* ranks) {
+    if (d < 1) return fail_msg(2, "tensor train needs at least one core (d = %d)", d);
+    if (p < 1 || p > kMaxP) return fail_msg(2, "basis size p = %d outside 1..%d", p, kMaxP);
+    if (!ranks) return fail_msg(2, "ranks is null");
+    if (ranks[0] != 1 || ranks[d] != 1) return fail_msg(2, "boundary ranks must be 1 (got %d, %d)", ranks[0], ranks[d]);
+    for (int j = 0; j <= d; j++)
+        if (ranks[j] < 1 || ranks[j] > kMaxR) return fail_msg(2, "rank %d = %d outside 1..%d", j, ranks[j], kMaxR);
+    return 0;
+}
+
+// Lay the train out in c->cores / c->meta and upload the packed host cores.
+int train_upload(bsde_ctx* c, Train& T, int d, int p, const int* ranks, const int* cap_ranks, const double* cores_host) {
+    T.d = d; T.p = p;
+    T.ranks.assign(ranks, ranks + d + 1);
+    T.cap.assign(cap_ranks ? cap_ranks : ranks, (cap_ranks ? cap_ranks : ranks) + d + 1);
+    T.off.resize(d);
+    int64_t o = 0;
+    for (int j = 0; j < d; j++) { T.off[j] = o; o += (int64_t)T.cap[j] * p * T.cap[j + 1]; }
+    T.total = o;
+    BSDE_TRY(c->cores.ensure(sizeof(double) * (size_t)o));
+    BSDE_TRY(c->meta.ensure(sizeof(int64_t) * d + sizeof(int) * (d + 1) + 64));
+    T.cores = c->cores.as<double>();
+    T.off_dev = c->meta.as<int64_t>();
+    T.ranks_dev = (int*)(T.off_dev + d);
+    BSDE_CUDA_OK(cudaMemcpyAsync(T.off_dev, T.off.data(), sizeof(int64_t) * d, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(T.ranks_dev, T.ranks.data(), sizeof(int) * (d + 1), cudaMemcpyHostToDevice, c->stream));
+    if (cores_host) {
+        bool packed = true;
+        for (int j = 0; j <= d; j++) packed = packed && T.cap[j] == T.ranks[j];
+        if (packed) {
+            BSDE_CUDA_OK(cudaMemcpyAsync(T.cores, cores_host, sizeof(double) * (size_t)o, cudaMemcpyHostToDevice, c->stream));
+        } else {
+            int64_t ho = 0;
+            for (int j = 0; j < d; j++) {
+                BSDE_CUDA_OK(cudaMemcpyAsync(T.core(j), cores_host + ho, sizeof(double) * (size_t)T.size(j), cudaMemcpyHostToDevice, c->stream));
+                ho += T.size(j);
+            }
+        }
+    }
+    // the host vectors above must outlive the async copies
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int train_download(bsde_ctx* c, const Train& T, double* cores_host) {
+    int64_t ho = 0;
+    for (int j = 0; j < T.d; j++) {
+        BSDE_CUDA_OK(cudaMemcpyAsync(cores_host + ho, T.core(j), sizeof(double) * (size_t)T.size(j), cudaMemcpyDeviceToHost, c->stream));
+        ho += T.size(j);
+    }
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int make_inputs(bsde_ctx* c, Inputs& in, int basis_kind, int d, int p, int64_t N, const double* data, const double* ddata,
+                const double* coef_host) {
+    if (basis_kind < 0 || basis_kind > 2) return fail_msg(2, "unknown basis_kind %d", basis_kind);
+    if (N < 1) return fail_msg(2, "sample count N = %lld must be positive", (long long)N);
+    if (!data) return fail_msg(2, "inputs pointer is null");
+    in.kind = basis_kind; in.p = p; in.d = d; in.N = N; in.data = data; in.ddata = ddata; in.coef = nullptr;
+    if (basis_kind == BASIS_LEGENDRE) {
+        if (!coef_host) return fail_msg(2, "Legendre basis needs coef_host ([3][p][p])");
+        BSDE_TRY(c->coef.ensure(sizeof(double) * 3 * p * p));
+        BSDE_CUDA_OK(cudaMemcpyAsync(c->coef.p, coef_host, sizeof(double) * 3 * p * p, cudaMemcpyHostToDevice, c->stream));
+        BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+        in.coef = c->coef.as<double>();
+    }
+    return 0;
+}
+
+// bond[k], k = 1..d-1: the interface living on the bond between core k-1 and core k (cap[k] slabs of N doubles).
+// It holds L_k (left interface entering core k) or R_{k-1} (right interface of core k-1) — never both at once.
+struct Bonds {
+    std::vector<double*> b;
+    double* at(int k) const { return b[k]; }
+};
+
+int bonds_alloc(bsde_ctx* c, const Train& T, int64_t N, Bonds& B) {
+    size_t tot = 0;
+    for (int k = 1; k < T.d; k++) tot += (size_t)T.cap[k] * N;
+    BSDE_TRY(c->bond.ensure(sizeof(double) * (tot ? tot : 1)));
+    B.b.assign(T.d + 1, nullptr);
+    double* q = c->bond.as<double>();
+    for (int k = 1; k < T.d; k++) { B.b[k] = q; q += (size_t)T.cap[k] * N; }
+    return 0;
+}
+
+// R_{j-1} for j = d-1 .. stop  (bond[j] <- core_j applied to bond[j+1])
+int build_right(bsde_ctx* c, const Train& T, const Inputs& in, const Bonds& B, int stop) {
+    for (int j = T.d - 1; j >= stop && j >= 1; j--) {
+        BSDE_TRY(launch_interface_right(in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == T.d - 1 ? nullptr : B.at(j + 1),
+                                        B.at(j), c->stream));
+        c->launches++;
+    }
+    return 0;
+}
+
+// L_{j+1} for j = 0 .. upto-1   (bond[j+1] <- bond[j] applied to core_j)
+int build_left(bsde_ctx* c, const Train& T, const Inputs& in, const Bonds& B, int upto) {
+    for (int j = 0; j < upto && j < T.d - 1; j++) {
+        BSDE_TRY(launch_interface_left(in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == 0 ? nullptr : B.at(j), B.at(j + 1),
+                                       c->stream));
+        c->launches++;
+    }
+    return 0;
+}
+
+int allreduce_moments(bsde_ctx* c, double* moments, int n) {
+    if (c->world <= 1) return 0;
+    const int rc = g_nccl.AllReduce(moments, moments, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
+    if (rc) return fail_msg(3, "ncclAllReduce failed: %s", g_nccl.GetErrorString(rc));
+    c->launches++;
+    return 0;
+}
+
+struct MicroCtx {
+    const Train* T;
+    const Inputs* in;
+    const Bonds* B;
+    const double* y;
+    int solver;
+    int mono;
+    int* info;
+};
+
+// assembly + (all-reduce) + solve/QR of core j; direction as MicroSolveArgs
+int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridge, const double* reg_diag, double* dbg) {
+    const Train& T = *m.T;
+    const int rl = T.ranks[j], rr = T.ranks[j + 1];
+    const AsmPlan* P;
+    BSDE_TRY(get_plan(c, rl, T.p, rr, m.mono, m.in->N, &P));
+    BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
+    BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->n_mom));
+    BSDE_TRY(launch_assembly(*P, *m.in, j, j == 0 ? nullptr : m.B->at(j), j == T.d - 1 ? nullptr : m.B->at(j + 1), m.y,
+                             c->partial.as<double>(), c->moments.as<double>(), c->stream));
+    c->launches += 2;
+    BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), P->n_mom));
+    MicroSolveArgs a{};
+    a.moments = c->moments.as<double>();
+    a.rl = rl; a.p = T.p; a.rr = rr; a.mono = m.mono; a.nLL = P->nLL; a.nRR = P->nRR; a.nB = P->nB;
+    a.direction = direction; a.solver = m.solver;
+    a.core_j = T.core(j);
+    a.core_nb = nullptr; a.r_nb = 1;
+    if (direction > 0) { a.core_nb = T.core(j + 1); a.r_nb = T.ranks[j + 2]; }
+    if (direction < 0) { a.core_nb = T.core(j - 1); a.r_nb = T.ranks[j - 1]; }
+    a.ridge = ridge; a.reg_diag = reg_diag; a.dbg_A = dbg; a.info = m.info;
+    BSDE_TRY(launch_micro_solve(a, c->stream));
+    c->launches++;
+    return 0;
+}
+
+// one ALS sweep: als.py:61-94
+int als_sweep(bsde_ctx* c, const MicroCtx& m) {
+    const Train& T = *m.T;
+    const int d = T.d;
+    for (int j = 0; j < d - 1; j++) {
+        BSDE_TRY(micro_step(c, m, j, +1, 0.0, nullptr, nullptr));
+        BSDE_TRY(launch_interface_left(*m.in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == 0 ? nullptr : m.B->at(j),
+                                       m.B->at(j + 1), c->stream));
+        c->launches++;
+    }
+    for (int j = d - 1; j >= 1; j--) {
+        BSDE_TRY(micro_step(c, m, j, -1, 0.0, nullptr, nullptr));
+        BSDE_TRY(launch_interface_right(*m.in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == d - 1 ? nullptr : m.B->at(j + 1),
+                                        m.B->at(j), c->stream));
+        c->launches++;
+    }
+    return 0;
+}
+
+int info_reset(bsde_ctx* c, int** info) {
+    BSDE_TRY(c->scalars.ensure(256));
+    *info = c->scalars.as<int>() + 16;
+    const int init[4] = {0, 0, 0, INT_MAX};
+    BSDE_CUDA_OK(cudaMemcpyAsync(*info, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
+            const double* y_dev, int n_iter, const int* ranks, int solver_id, double* cores_host, int* info_host) {
+    BSDE_TRY(check_ranks(d, p, ranks));
+    if (!y_dev || !cores_host) return fail_msg(2, "fit_als: null y or cores pointer");
+    if (n_iter < 0) return fail_msg(2, "fit_als: n_iter = %d", n_iter);
+    if (solver_id < 0 || solver_id > 3) return fail_msg(2, "Unknown method %d", solver_id);
+    for (int j = 0; j < d; j++) {
+        if (ranks[j] * p * ranks[j + 1] > kMaxN) return fail_msg(2, "core %d has %d unknowns (limit %d)", j, ranks[j] * p * ranks[j + 1], kMaxN);
+        if (ranks[j] > 8 || ranks[j + 1] > 8) return fail_msg(2, "ALS supports ranks <= 8 (core %d is %d x %d)", j, ranks[j], ranks[j + 1]);
+    }
+    Inputs in;
+    BSDE_TRY(make_inputs(c, in, basis_kind, d, p, N, inputs_dev, nullptr, coef_host));
+    Train T;
+    BSDE_TRY(train_upload(c, T, d, p, ranks, nullptr, cores_host));
+    int* info;
+    BSDE_TRY(info_reset(c, &info));
+    if (d >= 2) {
+        // als.py:39 — tt.orthonormalize(mode="right", start=1)
+        BSDE_TRY(launch_orthonormalize_right(T.cores, T.off_dev, T.ranks_dev, p, d, 1, d - 1, c->stream));
+        c->launches++;
+        Bonds B;
+        BSDE_TRY(bonds_alloc(c, T, N, B));
+        BSDE_TRY(build_right(c, T, in, B, 1));
+        MicroCtx m{&T, &in, &B, y_dev, solver_id, basis_kind == BASIS_POLY ? 1 : 0, info};
+        int it = 0;
+        if (n_iter > 0) { BSDE_TRY(als_sweep(c, m)); it = 1; }     // also builds the assembly plans / workspaces
+        if (it < n_iter) {
+            if (c->use_graph && n_iter - it >= 2) {
+                cudaGraph_t graph = nullptr;
+                cudaGraphExec_t exec = nullptr;
+                const int64_t before = c->launches;
+                BSDE_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                const int rc = als_sweep(c, m);
+                cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+                const int64_t per_sweep = c->launches - before;
+                c->launches = before;
+                e = cudaGraphInstantiate(&exec, graph, 0);
+                if (e != cudaSuccess) { cudaGraphDestroy(graph); return fail_cuda(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+                for (; it < n_iter; it++) {
+                    e = cudaGraphLaunch(exec, c->stream);
+                    if (e != cudaSuccess) break;
+                    c->launches += per_sweep;
+                }
+                cudaGraphExecDestroy(exec);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) return fail_cuda(e, "cudaGraphLaunch", __FILE__, __LINE__);
+            } else {
+                for (; it < n_iter; it++) BSDE_TRY(als_sweep(c, m));
+            }
+        }
+    }
+    BSDE_TRY(train_download(c, T, cores_host));
+    if (info_host) {
+        BSDE_CUDA_OK(cudaMemcpy(info_host, info, sizeof(int) * 4, cudaMemcpyDeviceToHost));
+        if (info_host[3] == INT_MAX) info_host[3] = 0;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ================================================ C ABI ================================================
+extern "C" {
+
+const char* bsde_last_error(void) { return g_err.c_str(); }
+int bsde_version(void) { return 100; }
+
+int bsde_ctx_create(int device, bsde_ctx** out) {
+    if (!out) return fail_msg(2, "bsde_ctx_create: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail_msg(4, "no CUDA device available (%s) — this backend has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail_msg(2, "device %d out of range (0..%d)", device, count - 1);
+    BSDE_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BSDE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail_msg(4, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    bsde_ctx* c = new bsde_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    BSDE_CUDA_OK(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+    c->stream = c->own;
+    *out = c;
+    return 0;
+}
+
+int bsde_ctx_destroy(bsde_ctx* c) {
+    if (!c) return 0;
+    Guard g(c);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto& kv : c->plans) asm_plan_free(kv.second);
+    for (DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg})
+        b->release();
+    cudaStreamDestroy(c->own);
+    delete c;
+    return 0;
+}
+
+int bsde_ctx_set_stream(bsde_ctx* c, void* cuda_stream) {
+    BSDE_CHECK_CTX(c);
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own;
+    return 0;
+}
+
+int bsde_ctx_sync(bsde_ctx* c) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bsde_ctx_launch_count(bsde_ctx* c, int64_t* out) {
+    BSDE_CHECK_CTX(c);
+    if (out) *out = c->launches;
+    return 0;
+}
+
+int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
+    BSDE_CHECK_CTX(c);
+    if (name && !strcmp(name, "use_graph")) { c->use_graph = value; return 0; }
+    return fail_msg(2, "unknown option '%s'", name ? name : "(null)");
+}
+
+int bsde_comm_unique_id(void* out128) {
+    if (!out128) return fail_msg(2, "bsde_comm_unique_id: out is null");
+    BSDE_TRY(nccl_load());
+    ncclUniqueId_ id;
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc) return fail_msg(3, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(rc));
+    memcpy(out128, &id, 128);
+    return 0;
+}
+
+int bsde_comm_init(bsde_ctx* c, const void* id128, int rank, int world) {
+    BSDE_CHECK_CTX(c);
+    if (world < 1 || rank < 0 || rank >= world) return fail_msg(2, "bsde_comm_init: rank %d of %d", rank, world);
+    if (world == 1) { c->rank = 0; c->world = 1; return 0; }
+    if (!id128) return fail_msg(2, "bsde_comm_init: id is null");
+    BSDE_TRY(nccl_load());
+    Guard g(c);
+    ncclUniqueId_ id;
+    memcpy(&id, id128, 128);
+    const int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (rc) return fail_msg(3, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(rc));
+    c->rank = rank; c->world = world;
+    return 0;
+}
+
+int bsde_malloc(bsde_ctx* c, int64_t bytes, void** out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (!out_dev || bytes < 0) return fail_msg(2, "bsde_malloc: bad arguments");
+    BSDE_CUDA_OK(cudaMalloc(out_dev, (size_t)(bytes ? bytes : 1)));
+    return 0;
+}
+
+int bsde_free(bsde_ctx* c, void* ptr_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    BSDE_CUDA_OK(cudaFree(ptr_dev));
+    return 0;
+}
+
+int bsde_memcpy_h2d(bsde_ctx* c, void* dst_dev, const void* src_host, int64_t bytes) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_CUDA_OK(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bsde_memcpy_d2h(bsde_ctx* c, void* dst_host, const void* src_dev, int64_t bytes) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_CUDA_OK(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int bsde_transpose(bsde_ctx* c, const double* src_dev, int64_t rows, int64_t cols, double* dst_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_TRY(launch_transpose(src_dev, rows, cols, dst_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int bsde_fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
+                 const double* y_dev, int n_iter, const int* ranks, int solver_id, double* cores_host, int* info_host) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    return fit_als(c, basis_kind, d, p, N, inputs_dev, coef_host, y_dev, n_iter, ranks, solver_id, cores_host, info_host);
+}
+
+int bsde_fit_als_host(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_host,
+                      const double* coef_host, const double* y_host, int n_iter, const int* ranks, int solver_id,
+                      double* cores_host, int* info_host) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (!inputs_host || !y_host) return fail_msg(2, "fit_als_host: null input pointer");
+    if (N < 1 || d < 1 || p < 1) return fail_msg(2, "fit_als_host: bad sizes");
+    const size_t in_bytes = sizeof(double) * (size_t)d * (basis_kind == BSDE_BASIS_PHI ? p : 1) * (size_t)N;
+    BSDE_TRY(c->in_copy.ensure(in_bytes));
+    BSDE_TRY(c->y_copy.ensure(sizeof(double) * (size_t)N));
+    BSDE_CUDA_OK(cudaMemcpyAsync(c->in_copy.p, inputs_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(c->y_copy.p, y_host, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
+    return fit_als(c, basis_kind, d, p, N, c->in_copy.as<double>(), coef_host, c->y_copy.as<double>(), n_iter, ranks, solver_id,
+                   cores_host, info_host);
+}
+
+int bsde_fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
+                   const double* y_dev, int n_iter, int* ranks, const int* init_ranks, double omega, double freq_omega,
+                   double min_sv, int max_rank, int solver_id, int do_reg, double* cores_host, int64_t cores_capacity,
+                   double* state_out_host) {
+    BSDE_CHECK_CTX(c);
+    return fail_msg(5, "bsde_fit_salsa: not implemented yet");
+}
+
+int bsde_tt_eval(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
+                 const int* ranks, const double* cores_host, double* y_out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_TRY(check_ranks(d, p, ranks));
+    if (!cores_host || !y_out_dev) return fail_msg(2, "tt_eval: null pointer");
+    Inputs in;
+    BSDE_TRY(make_inputs(c, in, basis_kind, d, p, N, inputs_dev, nullptr, coef_host));
+    Train T;
+    BSDE_TRY(train_upload(c, T, d, p, ranks, nullptr, cores_host));
+    BSDE_TRY(launch_tt_eval(in, T.cores, T.off_dev, T.ranks_dev, T.max_rank(), y_out_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int bsde_tt_grad(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* dphi_dev,
+                 const double* coef_host, const int* ranks, const double* cores_host, double* z_out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_TRY(check_ranks(d, p, ranks));
+    if (!cores_host || !z_out_dev) return fail_msg(2, "tt_grad: null pointer");
+    if (basis_kind == BSDE_BASIS_PHI && !dphi_dev) return fail_msg(2, "tt_grad: explicit basis values need dphi_dev");
+    Inputs in;
+    BSDE_TRY(make_inputs(c, in, basis_kind, d, p, N, inputs_dev, dphi_dev, coef_host));
+    Train T;
+    BSDE_TRY(train_upload(c, T, d, p, ranks, nullptr, cores_host));
+    Bonds B;
+    BSDE_TRY(bonds_alloc(c, T, N, B));
+    BSDE_TRY(build_right(c, T, in, B, 1));           // bond[k] = R_{k-1}
+    const int rmax = T.max_rank();
+    BSDE_TRY(c->tmp.ensure(sizeof(double) * 2 * (size_t)rmax * N));
+    double* Lbuf[2] = {c->tmp.as<double>(), c->tmp.as<double>() + (size_t)rmax * N};
+    for (int i = 0; i < d; i++) {
+        const double* Lin = i == 0 ? nullptr : Lbuf[i & 1];
+        double* Lout = i == d - 1 ? nullptr : Lbuf[(i + 1) & 1];
+        BSDE_TRY(launch_grad_step(in, i, T.core(i), T.ranks[i], T.ranks[i + 1], Lin, i == d - 1 ? nullptr : B.at(i + 1), Lout,
+                                  z_out_dev + (size_t)i * N, c->stream));
+        c->launches++;
+    }
+    return 0;
+}
+
+static int model_params(int model_id, const double* params, double& r, double& sigma0) {
+    if (!params) return fail_msg(2, "model params is null");
+    if (model_id == BSDE_MODEL_BLACKSCHOLES) { r = params[0]; sigma0 = params[1]; return 0; }
+    if (model_id == BSDE_MODEL_HJB) { r = 0.0; sigma0 = params[0]; return 0; }
+    return fail_msg(2, "unknown model_id %d", model_id);
+}
+
+int bsde_paths_simulate(bsde_ctx* c, int model_id, const double* params, int d, int64_t N, int steps, double T,
+                        const double* x0_host, uint64_t seed, int64_t sample_offset, int replay, double* xi_dev,
+                        double* x_out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    double r, sigma0;
+    BSDE_TRY(model_params(model_id, params, r, sigma0));
+    if (d < 1 || N < 1 || steps < 1 || !x0_host || !x_out_dev) return fail_msg(2, "paths_simulate: bad arguments");
+    if (replay && !xi_dev) return fail_msg(2, "paths_simulate: replay needs xi_dev");
+    BSDE_TRY(c->tmp.ensure(sizeof(double) * d));
+    BSDE_CUDA_OK(cudaMemcpyAsync(c->tmp.p, x0_host, sizeof(double) * d, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    const double dt = T / steps;
+    BSDE_TRY(launch_paths(model_id, sigma0, sqrt(dt), d, N, steps, c->tmp.as<double>(), seed, sample_offset, replay, xi_dev,
+                          x_out_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int bsde_terminal(bsde_ctx* c, int model_id, const double* params, int d, int64_t N, const double* x_dev, double* g_out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    double r, sigma0;
+    BSDE_TRY(model_params(model_id, params, r, sigma0));
+    BSDE_TRY(launch_terminal(model_id, d, N, x_dev, g_out_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int bsde_target(bsde_ctx* c, int model_id, const double* params, int d, int64_t N, const double* x_dev, const double* y_dev,
+                const double* y_next_dev, const double* grad_dev, const double* xi_dev, double dt, int apply_sigma,
+                double* out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    double r, sigma0;
+    BSDE_TRY(model_params(model_id, params, r, sigma0));
+    if (!x_dev || !y_dev || !y_next_dev || !grad_dev || !out_dev) return fail_msg(2, "target: null pointer");
+    BSDE_TRY(launch_target(model_id, r, sigma0, dt, d, N, x_dev, y_dev, y_next_dev, grad_dev, xi_dev, apply_sigma, out_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+int bsde_mean(bsde_ctx* c, const double* v_dev, int64_t N, double* out_host) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (!v_dev || !out_host || N < 1) return fail_msg(2, "mean: bad arguments");
+    const int nb = mean_grid(N);
+    BSDE_TRY(c->tmp.ensure(sizeof(double) * (nb + 1)));
+    BSDE_TRY(launch_block_sums(v_dev, N, c->tmp.as<double>(), c->stream));
+    BSDE_TRY(launch_sum_partials(c->tmp.as<double>(), nb, 1, 1, c->tmp.as<double>() + nb, c->stream));
+    c->launches += 2;
+    double s = 0.0;
+    BSDE_CUDA_OK(cudaMemcpyAsync(&s, c->tmp.as<double>() + nb, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    *out_host = s / (double)N;
+    return 0;
+}
+
+int bsde_normal_eq(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
+                   const double* y_dev, const int* ranks, const double* cores_host, int j, double* A_host, double* b_host) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_TRY(check_ranks(d, p, ranks));
+    if (j < 0 || j >= d) return fail_msg(2, "normal_eq: core index %d outside 0..%d", j, d - 1);
+    if (ranks[j] > 8 || ranks[j + 1] > 8) return fail_msg(2, "normal_eq: ranks <= 8 supported");
+    const int n = ranks[j] * p * ranks[j + 1];
+    if (n > kMaxN) return fail_msg(2, "normal_eq: n = %d exceeds %d", n, kMaxN);
+    Inputs in;
+    BSDE_TRY(make_inputs(c, in, basis_kind, d, p, N, inputs_dev, nullptr, coef_host));
+    Train T;
+    BSDE_TRY(train_upload(c, T, d, p, ranks, nullptr, cores_host));
+    Bonds B;
+    BSDE_TRY(bonds_alloc(c, T, N, B));
+    BSDE_TRY(build_right(c, T, in, B, j + 1));       // bond[k] = R_{k-1} for k > j
+    BSDE_TRY(build_left(c, T, in, B, j));            // bond[k] = L_k for k <= j
+    int* info;
+    BSDE_TRY(info_reset(c, &info));
+    BSDE_TRY(c->dbg.ensure(sizeof(double) * ((size_t)n * n + n)));
+    MicroCtx m{&T, &in, &B, y_dev, SOLVER_LSTSQ, basis_kind == BASIS_POLY ? 1 : 0, info};
+    BSDE_TRY(micro_step(c, m, j, 0, 0.0, nullptr, c->dbg.as<double>()));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (A_host) BSDE_CUDA_OK(cudaMemcpy(A_host, c->dbg.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
+    if (b_host) BSDE_CUDA_OK(cudaMemcpy(b_host, c->dbg.as<double>() + (size_t)n * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int bsde_solve(bsde_ctx* c, int n, const double* A_host, const double* b_host, int solver_id, double* x_host, int* info_host) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (n < 1 || n > 100) return fail_msg(2, "solve: n = %d outside 1..100", n);
+    if (solver_id < 0 || solver_id > 3) return fail_msg(2, "Unknown method %d", solver_id);
+    if (!A_host || !b_host || !x_host) return fail_msg(2, "solve: null pointer");
+    BSDE_TRY(c->dbg.ensure(sizeof(double) * ((size_t)n * n + 2 * n)));
+    double* A = c->dbg.as<double>();
+    double* b = A + (size_t)n * n;
+    double* x = b + n;
+    BSDE_CUDA_OK(cudaMemcpyAsync(A, A_host, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(b, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    int* info;
+    BSDE_TRY(info_reset(c, &info));
+    MicroSolveArgs a{};
+    a.rl = n; a.p = 1; a.rr = 1; a.direction = 0; a.solver = solver_id;
+    a.core_j = x; a.info = info; a.A_direct = A; a.b_direct = b;
+    BSDE_TRY(launch_micro_solve(a, c->stream));
+    c->launches++;
+    BSDE_CUDA_OK(cudaMemcpyAsync(x_host, x, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (info_host) {
+        BSDE_CUDA_OK(cudaMemcpy(info_host, info, sizeof(int) * 4, cudaMemcpyDeviceToHost));
+        if (info_host[3] == INT_MAX) info_host[3] = 0;
+    }
+    return 0;
+}
+
+int bsde_orthonormalize(bsde_ctx* c, int d, int p, const int* ranks, double* cores_host, int mode, int start, int stop) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_TRY(check_ranks(d, p, ranks));
+    if (mode != 0 && mode != 1) return fail_msg(2, "orthogonality must be either 'left' or 'right'");
+    if (stop == -1) stop = d - 1;
+    if (start < 0 || stop > d - 1) return fail_msg(2, "orthonormalize: range %d..%d outside the train", start, stop);
+    Train T;
+    BSDE_TRY(train_upload(c, T, d, p, ranks, nullptr, cores_host));
+    if (mode == 1) BSDE_TRY(launch_orthonormalize_right(T.cores, T.off_dev, T.ranks_dev, p, d, start, stop, c->stream));
+    else BSDE_TRY(launch_orthonormalize_left(T.cores, T.off_dev, T.ranks_dev, p, d, start, stop, c->stream));
+    c->launches++;
+    BSDE_TRY(train_download(c, T, cores_host));
+    return 0;
+}
+
+int bsde_basis_eval(bsde_ctx* c, int basis_kind, int p, int64_t N, const double* x_dev, const double* coef_host, int deriv,
+                    double* out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (basis_kind != BSDE_BASIS_POLY && basis_kind != BSDE_BASIS_LEGENDRE) return fail_msg(2, "basis_eval: basis_kind %d has no evaluator", basis_kind);
+    if (deriv < 0 || deriv > 2) return fail_msg(2, "basis_eval: deriv = %d", deriv);
+    if (p < 1 || p > kMaxP) return fail_msg(2, "basis size p = %d outside 1..%d", p, kMaxP);
+    Inputs in;
+    BSDE_TRY(make_inputs(c, in, basis_kind, 1, p, N, x_dev, nullptr, coef_host));
+    BSDE_TRY(launch_basis_eval(in, deriv, out_dev, c->stream));
+    c->launches++;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,526 @@
+// K5 — the small dense algebra of one micro-step, entirely inside one CTA (no host round trip):
+//   * expansion of the moment tensors (assembly.cu) into the normal matrix A (n x n) and right-hand side b
+//   * solver(A, b, method)                       reference: core/optimisation/solve.py:6-19
+//       'lstsq' = numpy.linalg.lstsq(rcond=None): minimum-norm solution, singular values <= eps*n*s_max dropped.
+//         Fast path: equilibrated Cholesky with the forward substitution fused into the factorisation, taken only
+//         when the pivots prove the matrix is far from the truncation threshold (then lstsq == exact solve).
+//         Otherwise: one-sided Jacobi SVD of A with LAPACK gelsd's truncation rule (rank-deficient systems such
+//         as the step-0 fit where every sample is identical).
+//       'lu' / 'solve' / 'qr' = Gaussian elimination with partial pivoting.
+//   * Householder QR (LAPACK dgeqr2/dorg2r sign conventions) of the updated core and the push of the
+//     triangular factor into the neighbouring core            reference: als.py:70-77 and :87-94
+//   * right/left orthonormalisation of a whole train            reference: tensor_train.py:34-87
+#include "common.cuh"
+#include "kernels.cuh"
+#include <cfloat>
+
+namespace bsde {
+
+namespace {
+
+constexpr int kDenseThreads = 256;
+
+__device__ __forceinline__ int pair_index(int a, int b, int r) {   // a <= b < r, row-major upper triangle
+    return a * r - (a * (a - 1)) / 2 + (b - a);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Householder QR of M (m x k, row-major with leading dimension ld, m >= k) executed by ONE warp.
+// On exit M holds Q (m x k, explicit) and Rm (k x k, row-major, ld k) the upper-triangular factor.
+// Sign convention = LAPACK dlarfg: beta = -sign(alpha) * norm, so diag(R) may be negative exactly as numpy's qr.
+__device__ void warp_householder_qr(double* M, int m, int k, int ld, double* Rm, double* tau, double* vbuf) {
+    const int lane = threadIdx.x & 31;
+    for (int c = 0; c < k; c++) {
+        double ss = 0.0;
+        for (int i = c + 1 + lane; i < m; i += 32) ss = fma(M[i * ld + c], M[i * ld + c], ss);
+        ss = warp_sum(ss);
+        const double alpha = M[c * ld + c];
+        double t = 0.0, beta = alpha;
+        if (ss != 0.0) {
+            beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+            t = (beta - alpha) / beta;
+            const double sc = 1.0 / (alpha - beta);
+            for (int i = c + 1 + lane; i < m; i += 32) M[i * ld + c] *= sc;
+        }
+        __syncwarp();
+        if (lane == 0) { tau[c] = t; M[c * ld + c] = beta; }
+        __syncwarp();
+        // apply H = I - t v v^T (v_c = 1) to the trailing columns
+        for (int cc = c + 1; cc < k; cc++) {
+            double w = 0.0;
+            for (int i = c + 1 + lane; i < m; i += 32) w = fma(M[i * ld + c], M[i * ld + cc], w);
+            w = warp_sum(w) + M[c * ld + cc];
+            w *= t;
+            for (int i = c + 1 + lane; i < m; i += 32) M[i * ld + cc] = fma(-w, M[i * ld + c], M[i * ld + cc]);
+            __syncwarp();
+            if (lane == 0) M[c * ld + cc] -= w;
+            __syncwarp();
+        }
+    }
+    // R
+    for (int e = lane; e < k * k; e += 32) {
+        const int r = e / k, c = e % k;
+        Rm[e] = (c >= r) ? M[r * ld + c] : 0.0;
+    }
+    __syncwarp();
+    // Q = H_0 ... H_{k-1} [I_k; 0]  (dorg2r: backwards accumulation)
+    for (int c = k - 1; c >= 0; c--) {
+        const double t = tau[c];
+        for (int i = c + 1 + lane; i < m; i += 32) vbuf[i] = M[i * ld + c];
+        __syncwarp();
+        // columns cc > c currently hold Q columns restricted to rows >= c+1 (row c of them is zero before H_c)
+        for (int cc = c + 1; cc < k; cc++) {
+            double w = 0.0;
+            for (int i = c + 1 + lane; i < m; i += 32) w = fma(vbuf[i], M[i * ld + cc], w);
+            w = warp_sum(w) * t;      // row c of column cc is 0 before applying H_c
+            for (int i = c + 1 + lane; i < m; i += 32) M[i * ld + cc] = fma(-w, vbuf[i], M[i * ld + cc]);
+            if (lane == 0) M[c * ld + cc] = -w;
+            __syncwarp();
+        }
+        // column c itself: H_c e_c = e_c - t v
+        for (int i = c + 1 + lane; i < m; i += 32) M[i * ld + c] = -t * vbuf[i];
+        if (lane == 0) M[c * ld + c] = 1.0 - t;
+        for (int i = lane; i < c; i += 32) M[i * ld + c] = 0.0;
+        __syncwarp();
+    }
+}
+
+struct SolveScratch {
+    double* A;      // (n+1) x (n+1) augmented, row-major, ld = n+1
+    double* G;      // n x n column-major (Jacobi)        — aliases A
+    double* V;      // n x n column-major (Jacobi)
+    double* x;      // n
+    double* sc;     // n  equilibration
+    double* bvec;   // n  copy of b
+    double* red;    // n  scratch
+};
+
+__device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int ld, double* bvec) {
+    const int n = a.rl * a.p * a.rr;
+    if (a.A_direct) {    // bsde_solve: an explicit system instead of moments (rl = n, p = rr = 1)
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) A[(e / n) * ld + (e % n)] = a.A_direct[e];
+        for (int e = threadIdx.x; e < n; e += blockDim.x) bvec[e] = a.b_direct[e];
+        return;
+    }
+    const double* M1 = a.moments;
+    const double* M2 = a.moments + (size_t)a.nB * a.nLL * a.nRR;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int row = e / n, col = e % n;
+        const int a1 = row / (a.p * a.rr), m1 = (row / a.rr) % a.p, b1 = row % a.rr;
+        const int a2 = col / (a.p * a.rr), m2 = (col / a.rr) % a.p, b2 = col % a.rr;
+        const int lam = pair_index(min(a1, a2), max(a1, a2), a.rl);
+        const int rho = pair_index(min(b1, b2), max(b1, b2), a.rr);
+        const int beta = a.mono ? (m1 + m2) : pair_index(min(m1, m2), max(m1, m2), a.p);
+        double v = M1[((size_t)beta * a.nLL + lam) * a.nRR + rho];
+        if (row == col) {
+            if (a.reg_diag) v += a.reg_diag[row];
+            v += a.ridge;
+        }
+        A[row * ld + col] = v;
+    }
+    for (int row = threadIdx.x; row < n; row += blockDim.x) {
+        const int a1 = row / (a.p * a.rr), m1 = (row / a.rr) % a.p, b1 = row % a.rr;
+        const double v = M2[((size_t)m1 * a.rl + a1) * a.rr + b1];
+        bvec[row] = v;
+    }
+}
+
+// Equilibrated Cholesky of [A b; b^T .] (lower triangle, in place).  Returns false (uniformly) if a pivot shows
+// that A is too close to lstsq's truncation threshold for "exact solve == lstsq" to be guaranteed.
+__device__ bool cholesky_solve(SolveScratch& S, int n, double* xout) {
+    const int ld = n + 1;
+    double* A = S.A;
+    __shared__ double s_min, s_dmin, s_dmax;
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) {
+        double dmin = DBL_MAX, dmax = 0.0;
+        int bad = 0;
+        for (int i = 0; i < n; i++) {
+            const double d = A[i * ld + i];
+            if (!(d > 0.0) || !isfinite(d)) bad = 1;
+            dmin = fmin(dmin, d);
+            dmax = fmax(dmax, d);
+        }
+        s_dmin = dmin; s_dmax = dmax; s_bad = bad; s_min = 1.0;
+    }
+    __syncthreads();
+    if (s_bad) return false;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) S.sc[i] = 1.0 / sqrt(A[i * ld + i]);
+    __syncthreads();
+    // scale lower triangle and the b row (row n)
+    for (int e = threadIdx.x; e < (n + 1) * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        if (i == n) A[n * ld + j] = S.bvec[j] * S.sc[j];
+        else if (j <= i) A[i * ld + j] *= S.sc[i] * S.sc[j];
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const double thresh = (double)n * (double)n * 1e-12;
+    for (int k = 0; k < n; k++) {
+        const double piv = A[k * ld + k];
+        if (!(piv > 0.0)) return false;                       // uniform: every thread reads the same value
+        if (threadIdx.x == 0 && piv < s_min) s_min = piv;
+        const double inv = 1.0 / sqrt(piv);
+        __syncthreads();
+        for (int i = k + 1 + threadIdx.x; i <= n; i += blockDim.x) A[i * ld + k] *= inv;
+        if (threadIdx.x == 0) A[k * ld + k] = inv;            // keep the reciprocal of the diagonal of the factor
+        __syncthreads();
+        for (int i = k + 1 + ty; i <= n; i += 16) {
+            const double lik = A[i * ld + k];
+            const int jmax = (i < n) ? i : n - 1;
+            for (int j = k + 1 + tx; j <= jmax; j += 16) A[i * ld + j] = fma(-lik, A[j * ld + k], A[i * ld + j]);
+        }
+        __syncthreads();
+    }
+    if (!(s_min * (s_dmin / s_dmax) > thresh)) return false;
+    // back substitution  L^T xs = z  (z = row n of the factor), one warp; diag holds reciprocals
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double* z = A + n * ld;
+        for (int k = n - 1; k >= 0; k--) {
+            const double xk = z[k] * A[k * ld + k];
+            __syncwarp();
+            if (lane == 0) z[k] = xk;
+            for (int i = lane; i < k; i += 32) z[i] = fma(-A[k * ld + i], xk, z[i]);
+            __syncwarp();
+        }
+        for (int i = lane; i < n; i += 32) xout[i] = z[i] * S.sc[i];
+    }
+    __syncthreads();
+    return true;
+}
+
+// One-sided (Hestenes) Jacobi SVD of the n x n matrix held column-major in G; V accumulates the right vectors.
+// Then the minimum-norm least-squares solution with LAPACK gelsd's rule: drop s_i <= rcond * s_max, rcond = eps*n.
+__device__ int jacobi_lstsq(SolveScratch& S, int n, const double* bvec, double* xout) {
+    double* G = S.G;
+    double* V = S.V;
+    __shared__ int s_rot;
+    __shared__ double s_smax;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) V[e] = ((e / n) == (e % n)) ? 1.0 : 0.0;
+    __syncthreads();
+    const int m = (n + 1) & ~1;
+    const double tol = DBL_EPSILON * sqrt((double)n);
+    for (int sweep = 0; sweep < 40; sweep++) {
+        if (threadIdx.x == 0) s_rot = 0;
+        __syncthreads();
+        for (int step = 0; step < m - 1; step++) {
+            for (int k = warp; k < m / 2; k += nwarps) {
+                int p, q;
+                if (k == 0) { p = m - 1; q = step; }
+                else { p = (step + k) % (m - 1); q = (step - k + m - 1) % (m - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                if (q >= n) continue;
+                double* gp = G + (size_t)p * n;
+                double* gq = G + (size_t)q * n;
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    const double x = gp[i], y = gq[i];
+                    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+                }
+                al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+                if (fabs(ga) > tol * sqrt(al * be) && ga != 0.0) {
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                    for (int i = lane; i < n; i += 32) {
+                        const double x = gp[i], y = gq[i];
+                        gp[i] = c * x - s * y;
+                        gq[i] = s * x + c * y;
+                    }
+                    double* vp = V + (size_t)p * n;
+                    double* vq = V + (size_t)q * n;
+                    for (int i = lane; i < n; i += 32) {
+                        const double x = vp[i], y = vq[i];
+                        vp[i] = c * x - s * y;
+                        vq[i] = s * x + c * y;
+                    }
+                    if (lane == 0) s_rot = 1;
+                }
+            }
+            __syncthreads();
+        }
+        const int rot = s_rot;
+        __syncthreads();
+        if (!rot) break;
+    }
+    // singular values, projections u_i . b
+    double* sig = S.sc;
+    double* proj = S.x;
+    for (int c = warp; c < n; c += nwarps) {
+        const double* g = G + (size_t)c * n;
+        double ss = 0.0, pb = 0.0;
+        for (int i = lane; i < n; i += 32) { ss = fma(g[i], g[i], ss); pb = fma(g[i], bvec[i], pb); }
+        ss = warp_sum(ss); pb = warp_sum(pb);
+        if (lane == 0) { sig[c] = sqrt(ss); proj[c] = pb; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int c = 0; c < n; c++) mx = fmax(mx, sig[c]);
+        s_smax = mx;
+    }
+    __syncthreads();
+    const double cutoff = DBL_EPSILON * (double)n * s_smax;
+    int rank = 0;
+    for (int c = 0; c < n; c++) rank += (sig[c] > cutoff) ? 1 : 0;
+    // x = sum_c v_c (g_c . b) / sig_c^2
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double acc = 0.0;
+        for (int c = 0; c < n; c++)
+            if (sig[c] > cutoff) acc = fma(V[(size_t)c * n + i], proj[c] / (sig[c] * sig[c]), acc);
+        xout[i] = acc;
+    }
+    __syncthreads();
+    return rank;
+}
+
+// Gaussian elimination with partial pivoting on [A | b] (row-major, ld = n+1, b in column n).
+__device__ void lu_solve(SolveScratch& S, int n, double* xout) {
+    const int ld = n + 1;
+    double* A = S.A;
+    __shared__ int s_piv;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) A[i * ld + n] = S.bvec[i];
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        if (threadIdx.x == 0) {
+            int best = k; double bv = fabs(A[k * ld + k]);
+            for (int i = k + 1; i < n; i++) { const double v = fabs(A[i * ld + k]); if (v > bv) { bv = v; best = i; } }
+            s_piv = best;
+        }
+        __syncthreads();
+        const int pr = s_piv;
+        if (pr != k)
+            for (int j = threadIdx.x; j <= n; j += blockDim.x) { const double t = A[k * ld + j]; A[k * ld + j] = A[pr * ld + j]; A[pr * ld + j] = t; }
+        __syncthreads();
+        const double inv = 1.0 / A[k * ld + k];
+        __syncthreads();
+        for (int i = k + 1 + (threadIdx.x >> 4); i < n; i += 16) {
+            const double f = A[i * ld + k] * inv;
+            for (int j = k + 1 + (threadIdx.x & 15); j <= n; j += 16) A[i * ld + j] = fma(-f, A[k * ld + j], A[i * ld + j]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int k = n - 1; k >= 0; k--) {
+            const double xk = A[k * ld + n] / A[k * ld + k];
+            __syncwarp();
+            if (lane == 0) xout[k] = xk;
+            for (int i = lane; i < k; i += 32) A[i * ld + n] = fma(-A[i * ld + k], xk, A[i * ld + n]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kDenseThreads)
+k_micro_solve(MicroSolveArgs a) {
+    extern __shared__ double sm[];
+    const int n = a.rl * a.p * a.rr;
+    const int ld = n + 1;
+    SolveScratch S;
+    S.A = sm;                                   // (n+1)^2 : augmented normal equations / Jacobi G / QR work matrix
+    S.G = sm;
+    S.V = sm + (size_t)(n + 1) * (n + 1);       // n^2     : Jacobi right vectors
+    S.x = S.V + (size_t)n * n;                  // n
+    S.sc = S.x + n;                             // n
+    S.bvec = S.sc + n;                          // n
+    S.red = S.bvec + n;                         // n       : Jacobi solution scratch
+    double* W = S.red + n;                      // kMaxR*kMaxP*kMaxR : neighbour-core product
+    double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
+    double* tau = qrR + kMaxR * kMaxR;          // kMaxR
+    double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
+    __shared__ int s_path, s_rank;
+
+    expand_normal_equations(a, S.A, ld, S.bvec);
+    __syncthreads();
+    if (a.dbg_A) {
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) a.dbg_A[e] = S.A[(e / n) * ld + (e % n)];
+        for (int e = threadIdx.x; e < n; e += blockDim.x) a.dbg_A[n * n + e] = S.bvec[e];
+    }
+    __syncthreads();
+    if (a.solver == SOLVER_LSTSQ) {
+        const bool ok = cholesky_solve(S, n, S.x);
+        if (threadIdx.x == 0) { s_path = ok ? 0 : 1; s_rank = n; }
+        if (!ok) {
+            __syncthreads();
+            // rebuild A (column-major == row-major, A is symmetric) with ld = n for the Jacobi path
+            expand_normal_equations(a, S.G, n, S.bvec);
+            __syncthreads();
+            double* xtmp = S.red;
+            const int rank = jacobi_lstsq(S, n, S.bvec, xtmp);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) S.x[i] = xtmp[i];
+            if (threadIdx.x == 0) s_rank = rank;
+            __syncthreads();
+        }
+    } else {
+        lu_solve(S, n, S.x);
+        if (threadIdx.x == 0) { s_path = 2; s_rank = n; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && a.info) {          // counters: [0] cholesky, [1] jacobi, [2] lu, [3] min numerical rank
+        a.info[s_path] += 1;
+        if (s_rank < a.info[3]) a.info[3] = s_rank;
+    }
+
+    // ---- orthogonalisation step of the sweep (als.py:70-77 / :87-94) ----
+    double* Mq = S.A;   // the factorisation storage is free now
+    if (a.direction == 0) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) a.core_j[i] = S.x[i];
+        return;
+    }
+    if (a.direction > 0) {
+        const int mrows = a.rl * a.p, k = a.rr;            // left_unfold(X): (rl*p) x rr, row-major == x itself
+        for (int i = threadIdx.x; i < n; i += blockDim.x) Mq[i] = S.x[i];
+        __syncthreads();
+        if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) a.core_j[i] = Mq[i];
+        // core_{j+1} <- S @ right_unfold(core_{j+1})   (rr x (p*r_nb))
+        const int cols = a.p * a.r_nb;
+        for (int e = threadIdx.x; e < k * cols; e += blockDim.x) {
+            const int r = e / cols, c = e % cols;
+            double acc = 0.0;
+            for (int t = r; t < k; t++) acc = fma(qrR[r * k + t], a.core_nb[t * cols + c], acc);
+            W[e] = acc;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < k * cols; e += blockDim.x) a.core_nb[e] = W[e];
+    } else {
+        const int mrows = a.p * a.rr, k = a.rl;            // right_unfold(X)^T: (p*rr) x rl
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int r = e / k, c = e % k;                 // Mq[r][c] = X[c][r]
+            Mq[e] = S.x[c * mrows + r];
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {   // core_j = Q^T
+            const int c = e / mrows, r = e % mrows;
+            a.core_j[e] = Mq[r * k + c];
+        }
+        // core_{j-1} <- left_unfold(core_{j-1}) @ S^T     ((r_nb*p) x rl)
+        const int rows = a.r_nb * a.p;
+        for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
+            const int r = e / k, c = e % k;
+            double acc = 0.0;
+            for (int t = c; t < k; t++) acc = fma(a.core_nb[r * k + t], qrR[c * k + t], acc);
+            W[e] = acc;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * k; e += blockDim.x) a.core_nb[e] = W[e];
+    }
+}
+
+// Whole-train orthonormalisation by successive QRs (tensor_train.py:34-87), one CTA, cores in global memory.
+struct OrthoArgs {
+    double* cores;
+    const int64_t* off;   // device
+    const int* ranks;     // device
+    int p, d, start, stop, right;
+};
+
+__global__ void __launch_bounds__(kDenseThreads)
+k_orthonormalize(OrthoArgs a) {
+    extern __shared__ double sm[];
+    double* Mq = sm;                               // up to kMaxR*kMaxP*kMaxR
+    double* W = Mq + kMaxR * kMaxP * kMaxR;
+    double* qrR = W + kMaxR * kMaxP * kMaxR;
+    double* tau = qrR + kMaxR * kMaxR;
+    double* vbuf = tau + kMaxR;
+    const int p = a.p;
+    if (a.right) {
+        for (int k = a.stop; k > a.start; k--) {
+            double* cur = a.cores + a.off[k];
+            double* prev = a.cores + a.off[k - 1];
+            const int rl = a.ranks[k], rr = a.ranks[k + 1], rp = a.ranks[k - 1];
+            const int mrows = p * rr, kk = rl, n = rl * p * rr;
+            for (int e = threadIdx.x; e < n; e += blockDim.x) { const int r = e / kk, c = e % kk; Mq[e] = cur[c * mrows + r]; }
+            __syncthreads();
+            if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, kk, kk, qrR, tau, vbuf);
+            __syncthreads();
+            for (int e = threadIdx.x; e < n; e += blockDim.x) { const int c = e / mrows, r = e % mrows; cur[e] = Mq[r * kk + c]; }
+            const int rows = rp * p;
+            for (int e = threadIdx.x; e < rows * kk; e += blockDim.x) {
+                const int r = e / kk, c = e % kk;
+                double acc = 0.0;
+                for (int t = c; t < kk; t++) acc = fma(prev[r * kk + t], qrR[c * kk + t], acc);
+                W[e] = acc;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < rows * kk; e += blockDim.x) prev[e] = W[e];
+            __syncthreads();
+        }
+    } else {
+        for (int k = a.start; k < a.stop; k++) {
+            double* cur = a.cores + a.off[k];
+            double* next = a.cores + a.off[k + 1];
+            const int rl = a.ranks[k], rr = a.ranks[k + 1], rn = a.ranks[k + 2];
+            const int mrows = rl * p, kk = rr, n = rl * p * rr;
+            for (int e = threadIdx.x; e < n; e += blockDim.x) Mq[e] = cur[e];
+            __syncthreads();
+            if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, kk, kk, qrR, tau, vbuf);
+            __syncthreads();
+            for (int e = threadIdx.x; e < n; e += blockDim.x) cur[e] = Mq[e];
+            const int cols = p * rn;
+            for (int e = threadIdx.x; e < kk * cols; e += blockDim.x) {
+                const int r = e / cols, c = e % cols;
+                double acc = 0.0;
+                for (int t = r; t < kk; t++) acc = fma(qrR[r * kk + t], next[t * cols + c], acc);
+                W[e] = acc;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < kk * cols; e += blockDim.x) next[e] = W[e];
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace
+
+int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st) {
+    const int n = a.rl * a.p * a.rr;
+    if (n > kMaxN) return fail_msg(2, "micro_solve: n = %d unknowns exceeds the in-CTA solver limit %d", n, kMaxN);
+    if (a.direction > 0 && a.rl * a.p < a.rr) return fail_msg(2, "micro_solve: left QR needs r_j*p >= r_{j+1} (%d*%d < %d)", a.rl, a.p, a.rr);
+    if (a.direction < 0 && a.p * a.rr < a.rl) return fail_msg(2, "micro_solve: right QR needs p*r_{j+1} >= r_j (%d*%d < %d)", a.p, a.rr, a.rl);
+    // keep in sync with the layout at the top of k_micro_solve
+    const size_t doubles = (size_t)(n + 1) * (n + 1) + (size_t)n * n + 4 * (size_t)n + kMaxR * kMaxP * kMaxR +
+                           kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16;
+    const size_t bytes = doubles * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BSDE_CUDA_OK(cudaFuncSetAttribute(k_micro_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    if (bytes > 220 * 1024) return fail_msg(2, "micro_solve: n = %d needs %zu B of shared memory", n, bytes);
+    k_micro_solve<<<1, kDenseThreads, bytes, st>>>(a);
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_ortho(double* cores, const int64_t* off_dev, const int* ranks_dev, int p, int d, int start, int stop,
+                        int right, cudaStream_t st) {
+    OrthoArgs a{cores, off_dev, ranks_dev, p, d, start, stop, right};
+    const size_t bytes = sizeof(double) * (2 * kMaxR * kMaxP * kMaxR + kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16);
+    k_orthonormalize<<<1, kDenseThreads, bytes, st>>>(a);
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_orthonormalize_right(double* cores, const int64_t* off_dev, const int* ranks_dev, int p, int d, int start,
+                                int stop, cudaStream_t st) {
+    return launch_ortho(cores, off_dev, ranks_dev, p, d, start, stop, 1, st);
+}
+int launch_orthonormalize_left(double* cores, const int64_t* off_dev, const int* ranks_dev, int p, int d, int start,
+                               int stop, cudaStream_t st) {
+    return launch_ortho(cores, off_dev, ranks_dev, p, d, start, stop, 0, st);
+}
+
+}  // namespace bsde

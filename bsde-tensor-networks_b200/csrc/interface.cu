@@ -1,0 +1,364 @@
+// K3 / K6 / K7 — per-sample contractions of the tensor train with the basis values.
+//
+//   k_interface_left   L_{j+1}[s,b] = sum_{a,m} L_j[s,a] phi_j[s,m] C_j[a,m,b]        (als.py:14-17 chained)
+//   k_interface_right  R_{j-1}[s,a] = sum_{m,b} C_j[a,m,b] phi_j[s,m] R_j[s,b]
+//   k_tt_eval          V(x_s) = G_0[s] G_1[s] ... G_{d-1}[s]                            (utils.py:19-27)
+//   k_grad_step        dV/dx_i(x_s) = L_i[s] (C_i . dphi_i[s]) R_i[s]  (+ L_{i+1})      (derivative.py:43-85)
+//   k_residual         sum_s ((L_j (x) phi_j (x) R_j)[s] . c_j - y_s)^2                 (als.py:168-172, 288-293)
+//
+// All are HBM-bound streaming kernels: one thread per sample, sample-contiguous (coalesced) loads and
+// stores, the core broadcast from shared memory, basis values evaluated in registers (never stored).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace bsde {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t N) {
+    int64_t b = (N + kThreads - 1) / kThreads;
+    const int64_t cap = 148 * 16;
+    return (int)(b < cap ? b : cap);
+}
+
+template <int RB, int PB>
+__global__ void __launch_bounds__(kThreads)
+k_interface_left(Inputs in, int j, const double* __restrict__ core, int r_in, int r_out,
+                 const double* __restrict__ Lin, double* __restrict__ Lout) {
+    extern __shared__ double csm[];
+    const int p = in.p;
+    for (int i = threadIdx.x; i < r_in * p * r_out; i += blockDim.x) csm[i] = core[i];
+    __syncthreads();
+    const int64_t N = in.N;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        double phi[PB];
+        basis_values<PB>(in, j, s, 0, phi);
+        double acc[RB];
+#pragma unroll
+        for (int b = 0; b < RB; b++) acc[b] = 0.0;
+        for (int a = 0; a < r_in; a++) {
+            const double la = Lin ? Lin[(int64_t)a * N + s] : 1.0;
+#pragma unroll
+            for (int m = 0; m < PB; m++) {
+                if (m < p) {
+                    const double t = la * phi[m];
+                    const double* c = csm + (a * p + m) * r_out;
+#pragma unroll
+                    for (int b = 0; b < RB; b++)
+                        if (b < r_out) acc[b] = fma(t, c[b], acc[b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < RB; b++)
+            if (b < r_out) Lout[(int64_t)b * N + s] = acc[b];
+    }
+}
+
+template <int RB, int PB>
+__global__ void __launch_bounds__(kThreads)
+k_interface_right(Inputs in, int j, const double* __restrict__ core, int r_out, int r_in,
+                  const double* __restrict__ Rin, double* __restrict__ Rout) {
+    // core is (r_out, p, r_in); Rin has r_in components (null => ones(1)), Rout gets r_out components
+    extern __shared__ double csm[];
+    const int p = in.p;
+    for (int i = threadIdx.x; i < r_out * p * r_in; i += blockDim.x) csm[i] = core[i];
+    __syncthreads();
+    const int64_t N = in.N;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        double phi[PB];
+        basis_values<PB>(in, j, s, 0, phi);
+        double rb[RB];
+#pragma unroll
+        for (int b = 0; b < RB; b++) rb[b] = (b < r_in) ? (Rin ? Rin[(int64_t)b * N + s] : 1.0) : 0.0;
+        for (int a = 0; a < r_out; a++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < PB; m++) {
+                if (m < p) {
+                    const double* c = csm + (a * p + m) * r_in;
+                    double t = 0.0;
+#pragma unroll
+                    for (int b = 0; b < RB; b++)
+                        if (b < r_in) t = fma(c[b], rb[b], t);
+                    acc = fma(phi[m], t, acc);
+                }
+            }
+            Rout[(int64_t)a * N + s] = acc;
+        }
+    }
+}
+
+// v <- v . G_j for one core, all in registers.
+template <int RB, int PB>
+__device__ __forceinline__ void chain_step(double (&v)[RB], const double (&phi)[PB], const double* __restrict__ c,
+                                           int rl, int p, int rr) {
+    double nv[RB];
+#pragma unroll
+    for (int b = 0; b < RB; b++) nv[b] = 0.0;
+#pragma unroll
+    for (int a = 0; a < RB; a++) {
+        if (a < rl) {
+#pragma unroll
+            for (int m = 0; m < PB; m++) {
+                if (m < p) {
+                    const double t = v[a] * phi[m];
+#pragma unroll
+                    for (int b = 0; b < RB; b++)
+                        if (b < rr) nv[b] = fma(t, __ldg(c + (a * p + m) * rr + b), nv[b]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < RB; b++) v[b] = nv[b];
+}
+
+template <int RB, int PB>
+__global__ void __launch_bounds__(kThreads)
+k_tt_eval(Inputs in, const double* __restrict__ cores, const int64_t* __restrict__ core_off,
+          const int* __restrict__ ranks, double* __restrict__ out) {
+    const int64_t N = in.N;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        double v[RB];
+#pragma unroll
+        for (int b = 0; b < RB; b++) v[b] = (b == 0) ? 1.0 : 0.0;
+        for (int j = 0; j < in.d; j++) {
+            double phi[PB];
+            basis_values<PB>(in, j, s, 0, phi);
+            chain_step<RB, PB>(v, phi, cores + core_off[j], ranks[j], in.p, ranks[j + 1]);
+        }
+        out[s] = v[0];
+    }
+}
+
+// One asset of multi_derivative: z_i[s] = L_i . (C_i . dphi_i) . R_i, and L_{i+1} = L_i . (C_i . phi_i).
+template <int RB, int PB>
+__global__ void __launch_bounds__(kThreads)
+k_grad_step(Inputs in, int i, const double* __restrict__ core, int rl, int rr,
+            const double* __restrict__ Lin, const double* __restrict__ Rin,
+            double* __restrict__ Lout, double* __restrict__ z) {
+    extern __shared__ double csm[];
+    const int p = in.p;
+    for (int k = threadIdx.x; k < rl * p * rr; k += blockDim.x) csm[k] = core[k];
+    __syncthreads();
+    const int64_t N = in.N;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        double phi[PB], dphi[PB];
+        basis_values<PB>(in, i, s, 0, phi);
+        basis_values<PB>(in, i, s, 1, dphi);
+        double rb[RB], acc[RB];
+#pragma unroll
+        for (int b = 0; b < RB; b++) {
+            rb[b] = (b < rr) ? (Rin ? Rin[(int64_t)b * N + s] : 1.0) : 0.0;
+            acc[b] = 0.0;
+        }
+        double zz = 0.0;
+        for (int a = 0; a < rl; a++) {
+            const double la = Lin ? Lin[(int64_t)a * N + s] : 1.0;
+#pragma unroll
+            for (int m = 0; m < PB; m++) {
+                if (m < p) {
+                    const double* c = csm + (a * p + m) * rr;
+                    const double t = la * phi[m];
+                    double u = 0.0;
+#pragma unroll
+                    for (int b = 0; b < RB; b++) {
+                        if (b < rr) {
+                            acc[b] = fma(t, c[b], acc[b]);
+                            u = fma(c[b], rb[b], u);
+                        }
+                    }
+                    zz = fma(la * dphi[m], u, zz);
+                }
+            }
+        }
+        z[s] = zz;
+        if (Lout) {
+#pragma unroll
+            for (int b = 0; b < RB; b++)
+                if (b < rr) Lout[(int64_t)b * N + s] = acc[b];
+        }
+    }
+}
+
+// Deterministic block sum: warp shuffles, then warp partials combined in warp order.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) scratch[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += scratch[k];
+    return t;
+}
+
+// sum_s (pred_s - y_s)^2 with pred = (L (x) phi (x) R) . core ; optionally writes pred.
+template <int RB, int PB>
+__global__ void __launch_bounds__(kThreads)
+k_residual(Inputs in, int j, const double* __restrict__ core, int rl, int rr,
+           const double* __restrict__ Lin, const double* __restrict__ Rin, const double* __restrict__ y,
+           double* __restrict__ pred_out, double* __restrict__ partial) {
+    extern __shared__ double csm[];
+    __shared__ double scratch[kThreads / 32];
+    const int p = in.p;
+    for (int k = threadIdx.x; k < rl * p * rr; k += blockDim.x) csm[k] = core[k];
+    __syncthreads();
+    const int64_t N = in.N;
+    double loc = 0.0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        double phi[PB];
+        basis_values<PB>(in, j, s, 0, phi);
+        double rb[RB];
+#pragma unroll
+        for (int b = 0; b < RB; b++) rb[b] = (b < rr) ? (Rin ? Rin[(int64_t)b * N + s] : 1.0) : 0.0;
+        double pr = 0.0;
+        for (int a = 0; a < rl; a++) {
+            const double la = Lin ? Lin[(int64_t)a * N + s] : 1.0;
+#pragma unroll
+            for (int m = 0; m < PB; m++) {
+                if (m < p) {
+                    const double* c = csm + (a * p + m) * rr;
+                    double u = 0.0;
+#pragma unroll
+                    for (int b = 0; b < RB; b++)
+                        if (b < rr) u = fma(c[b], rb[b], u);
+                    pr = fma(la * phi[m], u, pr);
+                }
+            }
+        }
+        if (pred_out) pred_out[s] = pr;
+        if (y) {
+            const double e = pr - y[s];
+            loc = fma(e, e, loc);
+        }
+    }
+    const double t = block_sum(loc, scratch);
+    if (threadIdx.x == 0 && partial) partial[blockIdx.x] = t;
+}
+
+// out[e] = sum_p partial[p * stride + e]   (fixed order => bitwise reproducible)
+__global__ void k_sum_partials(const double* __restrict__ partial, int n_partials, int64_t stride, int n_elems,
+                               double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int q = 0;
+    for (; q + 3 < n_partials; q += 4) {
+        a0 += partial[(int64_t)q * stride + e];
+        a1 += partial[(int64_t)(q + 1) * stride + e];
+        a2 += partial[(int64_t)(q + 2) * stride + e];
+        a3 += partial[(int64_t)(q + 3) * stride + e];
+    }
+    for (; q < n_partials; q++) a0 += partial[(int64_t)q * stride + e];
+    out[e] = (a0 + a1) + (a2 + a3);
+}
+
+template <int RB>
+int pick_pb_left(int p, Inputs in, int j, const double* core, int r_in, int r_out, const double* Lin, double* Lout,
+                 cudaStream_t st) {
+    const size_t sm = sizeof(double) * r_in * p * r_out;
+    const int g = grid_for(in.N);
+    if (p <= 4) k_interface_left<RB, 4><<<g, kThreads, sm, st>>>(in, j, core, r_in, r_out, Lin, Lout);
+    else k_interface_left<RB, 8><<<g, kThreads, sm, st>>>(in, j, core, r_in, r_out, Lin, Lout);
+    return 0;
+}
+template <int RB>
+int pick_pb_right(int p, Inputs in, int j, const double* core, int r_out, int r_in, const double* Rin, double* Rout,
+                  cudaStream_t st) {
+    const size_t sm = sizeof(double) * r_in * p * r_out;
+    const int g = grid_for(in.N);
+    if (p <= 4) k_interface_right<RB, 4><<<g, kThreads, sm, st>>>(in, j, core, r_out, r_in, Rin, Rout);
+    else k_interface_right<RB, 8><<<g, kThreads, sm, st>>>(in, j, core, r_out, r_in, Rin, Rout);
+    return 0;
+}
+
+#define BSDE_DISPATCH_RB(R, CALL)                    \
+    do {                                             \
+        if ((R) <= 1) { CALL(1); }                   \
+        else if ((R) <= 2) { CALL(2); }              \
+        else if ((R) <= 4) { CALL(4); }              \
+        else if ((R) <= 8) { CALL(8); }              \
+        else { CALL(16); }                           \
+    } while (0)
+
+}  // namespace
+
+int launch_interface_left(const Inputs& in, int j, const double* core, int r_in, int r_out, const double* Lin,
+                          double* Lout, cudaStream_t st) {
+    if (in.p > kMaxP || r_in > kMaxR || r_out > kMaxR) return fail_msg(2, "interface_left: p=%d r=(%d,%d) exceeds limits", in.p, r_in, r_out);
+#define CALL(RBV) pick_pb_left<RBV>(in.p, in, j, core, r_in, r_out, Lin, Lout, st)
+    BSDE_DISPATCH_RB(r_out, CALL);
+#undef CALL
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_interface_right(const Inputs& in, int j, const double* core, int r_out, int r_in, const double* Rin,
+                           double* Rout, cudaStream_t st) {
+    if (in.p > kMaxP || r_in > kMaxR || r_out > kMaxR) return fail_msg(2, "interface_right: p=%d r=(%d,%d) exceeds limits", in.p, r_out, r_in);
+#define CALL(RBV) pick_pb_right<RBV>(in.p, in, j, core, r_out, r_in, Rin, Rout, st)
+    BSDE_DISPATCH_RB(r_in, CALL);
+#undef CALL
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_tt_eval(const Inputs& in, const double* cores, const int64_t* core_off, const int* ranks_dev, int max_rank,
+                   double* out, cudaStream_t st) {
+    if (in.p > kMaxP || max_rank > kMaxR) return fail_msg(2, "tt_eval: p=%d rank=%d exceeds limits", in.p, max_rank);
+    const int g = grid_for(in.N);
+#define CALL(RBV)                                                                                          \
+    if (in.p <= 4) k_tt_eval<RBV, 4><<<g, kThreads, 0, st>>>(in, cores, core_off, ranks_dev, out);         \
+    else k_tt_eval<RBV, 8><<<g, kThreads, 0, st>>>(in, cores, core_off, ranks_dev, out)
+    BSDE_DISPATCH_RB(max_rank, CALL);
+#undef CALL
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_grad_step(const Inputs& in, int i, const double* core, int rl, int rr, const double* Lin, const double* Rin,
+                     double* Lout, double* z, cudaStream_t st) {
+    if (in.p > kMaxP || rl > kMaxR || rr > kMaxR) return fail_msg(2, "grad_step: p=%d r=(%d,%d) exceeds limits", in.p, rl, rr);
+    const int g = grid_for(in.N);
+    const size_t sm = sizeof(double) * rl * in.p * rr;
+#define CALL(RBV)                                                                                               \
+    if (in.p <= 4) k_grad_step<RBV, 4><<<g, kThreads, sm, st>>>(in, i, core, rl, rr, Lin, Rin, Lout, z);          \
+    else k_grad_step<RBV, 8><<<g, kThreads, sm, st>>>(in, i, core, rl, rr, Lin, Rin, Lout, z)
+    BSDE_DISPATCH_RB(rr, CALL);
+#undef CALL
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int residual_grid(int64_t N) { return grid_for(N); }
+
+int launch_residual(const Inputs& in, int j, const double* core, int rl, int rr, const double* Lin, const double* Rin,
+                    const double* y, double* pred_out, double* partial, double* out_sum, cudaStream_t st) {
+    if (in.p > kMaxP || rl > kMaxR || rr > kMaxR) return fail_msg(2, "residual: p=%d r=(%d,%d) exceeds limits", in.p, rl, rr);
+    const int g = grid_for(in.N);
+    const size_t sm = sizeof(double) * rl * in.p * rr;
+#define CALL(RBV)                                                                                                       \
+    if (in.p <= 4) k_residual<RBV, 4><<<g, kThreads, sm, st>>>(in, j, core, rl, rr, Lin, Rin, y, pred_out, partial);       \
+    else k_residual<RBV, 8><<<g, kThreads, sm, st>>>(in, j, core, rl, rr, Lin, Rin, y, pred_out, partial)
+    BSDE_DISPATCH_RB(rr, CALL);
+#undef CALL
+    BSDE_CUDA_OK(cudaGetLastError());
+    if (partial && out_sum) {
+        k_sum_partials<<<1, 32, 0, st>>>(partial, g, 1, 1, out_sum);
+        BSDE_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_sum_partials(const double* partial, int n_partials, int64_t stride, int n_elems, double* out, cudaStream_t st) {
+    k_sum_partials<<<(n_elems + 127) / 128, 128, 0, st>>>(partial, n_partials, stride, n_elems, out);
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace bsde

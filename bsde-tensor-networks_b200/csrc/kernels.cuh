@@ -1,0 +1,85 @@
+// Host-callable launchers of the kernels (internal to the library; the public surface is include/bsde_b200.h).
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace bsde {
+
+// ---- interface.cu --------------------------------------------------------------------------------
+int launch_interface_left(const Inputs& in, int j, const double* core, int r_in, int r_out, const double* Lin,
+                          double* Lout, cudaStream_t st);
+int launch_interface_right(const Inputs& in, int j, const double* core, int r_out, int r_in, const double* Rin,
+                           double* Rout, cudaStream_t st);
+int launch_tt_eval(const Inputs& in, const double* cores, const int64_t* core_off, const int* ranks_dev, int max_rank,
+                   double* out, cudaStream_t st);
+int launch_grad_step(const Inputs& in, int i, const double* core, int rl, int rr, const double* Lin, const double* Rin,
+                     double* Lout, double* z, cudaStream_t st);
+int residual_grid(int64_t N);
+int launch_residual(const Inputs& in, int j, const double* core, int rl, int rr, const double* Lin, const double* Rin,
+                    const double* y, double* pred_out, double* partial, double* out_sum, cudaStream_t st);
+int launch_sum_partials(const double* partial, int n_partials, int64_t stride, int n_elems, double* out, cudaStream_t st);
+
+// ---- assembly.cu ---------------------------------------------------------------------------------
+// Plan of the moment GEMMs for one core shape (r_l, p, r_r, monomial?) — see assembly.cu.
+struct AsmPlan {
+    int rl = 0, p = 0, rr = 0, mono = 0;
+    int nLL = 0, nRR = 0, nB = 0;
+    int F = 0;                                    // staged per-sample functions
+    int fLL = 0, fRR = 0, fRow1 = 0, fL = 0, fR = 0, fRow2 = 0;   // first index of each family (0 = ZERO)
+    int n_jobs = 0, NJ = 0, n_groups = 0;         // 8x8 output tiles; tiles per warp; blockIdx.y groups
+    int n_mom = 0;                                // canonical moments: nB*nLL*nRR + p*rl*rr + 1
+    int n = 0;                                    // unknowns r_l*p*r_r
+    int grid_x = 0;                               // CTAs along the sample axis (= number of partial rows)
+    int64_t partial_stride = 0;                   // doubles per partial row = n_groups*NJ*64 + 1
+    size_t smem_bytes = 0;
+    uint16_t* d_tab = nullptr;                    // [n_groups*NJ][8][3]  (row fn, col fn 1, col fn 2) per lane group
+    uint8_t* d_flags = nullptr;                   // [n_groups*NJ] bit0 reload row, bit1 reload c1, bit2 reload c2
+    int32_t* d_gather = nullptr;                  // [n_mom] canonical moment -> slot in a partial row
+    std::vector<int32_t> h_gather;
+};
+
+int asm_plan_build(AsmPlan& plan, int rl, int p, int rr, int mono, int64_t N, int sm_count);
+void asm_plan_free(AsmPlan& plan);
+// Launches the assembly kernel and the partial reduction; `moments` (n_mom doubles, device) receives
+// [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y].
+int launch_assembly(const AsmPlan& plan, const Inputs& in, int j, const double* L, const double* R, const double* y,
+                    double* partial, double* moments, cudaStream_t st);
+
+// ---- dense.cu ------------------------------------------------------------------------------------
+enum SolverId : int { SOLVER_LSTSQ = 0, SOLVER_LU = 1, SOLVER_QR = 2, SOLVER_SOLVE = 3 };
+
+struct MicroSolveArgs {
+    const double* moments;   // canonical moments of core j
+    int rl, p, rr, mono, nLL, nRR, nB;
+    int direction;           // +1: left half-sweep (QR, push S right); -1: right half-sweep (push S^T left); 0: no QR
+    int solver;
+    double* core_j;          // (rl,p,rr) out
+    double* core_nb;         // neighbour core: j+1 (rr, p, r_nb) for +1 ; j-1 (r_nb, p, rl) for -1
+    int r_nb;                // the neighbour's far rank
+    double ridge;            // added to the diagonal (SALSA eta), 0 for ALS
+    const double* reg_diag;  // optional n-vector added to the diagonal (SALSA regulariser), may be null
+    double* dbg_A;           // optional n*n + n (A | b) dump for parity tests
+    int* info;               // accumulated: [0] cholesky solves, [1] jacobi-svd solves, [2] lu solves, [3] min numerical rank
+    const double* A_direct = nullptr;   // explicit n x n system (then rl = n, p = rr = 1 and moments is unused)
+    const double* b_direct = nullptr;
+};
+int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st);
+int launch_orthonormalize_right(double* cores, const int64_t* core_off_host, const int* ranks_host, int p, int d,
+                                int start, int stop, cudaStream_t st);
+int launch_orthonormalize_left(double* cores, const int64_t* core_off_host, const int* ranks_host, int p, int d,
+                               int start, int stop, cudaStream_t st);
+
+
+// ---- model.cu ------------------------------------------------------------------------------------
+int launch_paths(int model, double sigma0, double sqrt_dt, int d, int64_t N, int steps, const double* x0_dev,
+                 uint64_t seed, int64_t sample_offset, int replay, double* xi, double* x, cudaStream_t st);
+int launch_terminal(int model, int d, int64_t N, const double* x, double* out, cudaStream_t st);
+int launch_target(int model, double r, double sigma0, double dt, int d, int64_t N, const double* x, const double* y,
+                  const double* y_next, const double* grad, const double* xi, int apply_sigma, double* out,
+                  cudaStream_t st);
+int launch_transpose(const double* src, int64_t rows, int64_t cols, double* dst, cudaStream_t st);
+int launch_basis_eval(const Inputs& in, int deriv, double* out, cudaStream_t st);
+int mean_grid(int64_t N);
+int launch_block_sums(const double* v, int64_t N, double* partial, cudaStream_t st);
+
+}  // namespace bsde
