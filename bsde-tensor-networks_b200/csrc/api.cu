@@ -98,6 +98,16 @@ struct bsde_ctx {
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // per-kernel-class device timing (option "profile"): event pairs recorded around eager launches
+    int64_t profile = 0;
+    enum { P_ASSEMBLY = 0, P_REDUCE, P_ALLREDUCE, P_SOLVE, P_INTERFACE, P_CLASSES };
+    double prof_ms[P_CLASSES] = {0, 0, 0, 0, 0};
+    int64_t prof_n[P_CLASSES] = {0, 0, 0, 0, 0};
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    bool capturing = false;
 };
 
 namespace {
@@ -255,6 +265,39 @@ int build_left(bsde_ctx* c, const Train& T, const Inputs& in, const Bonds& B, in
     return 0;
 }
 
+// ---- profiling helpers: no-ops unless option "profile" is set and we are not capturing a graph ----
+cudaEvent_t prof_mark(bsde_ctx* c) {
+    if (!c->profile || c->capturing) return nullptr;
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->ev_pool.push_back(e);
+    }
+    cudaEvent_t e = c->ev_pool[c->ev_used++];
+    cudaEventRecord(e, c->stream);
+    return e;
+}
+cudaEvent_t prof_take(bsde_ctx* c) {     // an event to be recorded by someone else
+    if (!c->profile || c->capturing) return nullptr;
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+void prof_span(bsde_ctx* c, int cls, cudaEvent_t a, cudaEvent_t b) {
+    if (a && b) c->spans.push_back({cls, a, b});
+}
+void prof_collect(bsde_ctx* c) {         // after a stream synchronise
+    for (const auto& s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { c->prof_ms[s.cls] += ms; c->prof_n[s.cls]++; }
+    }
+    c->spans.clear();
+    c->ev_used = 0;
+}
+
 int allreduce_moments(bsde_ctx* c, double* moments, int n) {
     if (c->world <= 1) return 0;
     const int rc = g_nccl.AllReduce(moments, moments, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
@@ -281,10 +324,16 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     BSDE_TRY(get_plan(c, rl, T.p, rr, m.mono, m.in->N, &P));
     BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
     BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->n_mom));
+    cudaEvent_t e0 = prof_mark(c), e1 = prof_take(c);
     BSDE_TRY(launch_assembly(*P, *m.in, j, j == 0 ? nullptr : m.B->at(j), j == T.d - 1 ? nullptr : m.B->at(j + 1), m.y,
-                             c->partial.as<double>(), c->moments.as<double>(), c->stream));
+                             c->partial.as<double>(), c->moments.as<double>(), c->stream, e1));
     c->launches += 2;
+    cudaEvent_t e2 = prof_mark(c);
+    prof_span(c, bsde_ctx::P_ASSEMBLY, e0, e1);
+    prof_span(c, bsde_ctx::P_REDUCE, e1, e2);
     BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), P->n_mom));
+    cudaEvent_t e3 = c->world > 1 ? prof_mark(c) : e2;
+    if (c->world > 1) prof_span(c, bsde_ctx::P_ALLREDUCE, e2, e3);
     MicroSolveArgs a{};
     a.moments = c->moments.as<double>();
     a.rl = rl; a.p = T.p; a.rr = rr; a.mono = m.mono; a.nLL = P->nLL; a.nRR = P->nRR; a.nB = P->nB;
@@ -296,6 +345,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     a.ridge = ridge; a.reg_diag = reg_diag; a.dbg_A = dbg; a.info = m.info;
     BSDE_TRY(launch_micro_solve(a, c->stream));
     c->launches++;
+    prof_span(c, bsde_ctx::P_SOLVE, e3, prof_mark(c));
     return 0;
 }
 
@@ -305,15 +355,19 @@ int als_sweep(bsde_ctx* c, const MicroCtx& m) {
     const int d = T.d;
     for (int j = 0; j < d - 1; j++) {
         BSDE_TRY(micro_step(c, m, j, +1, 0.0, nullptr, nullptr));
+        cudaEvent_t e0 = prof_mark(c);
         BSDE_TRY(launch_interface_left(*m.in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == 0 ? nullptr : m.B->at(j),
                                        m.B->at(j + 1), c->stream));
         c->launches++;
+        prof_span(c, bsde_ctx::P_INTERFACE, e0, prof_mark(c));
     }
     for (int j = d - 1; j >= 1; j--) {
         BSDE_TRY(micro_step(c, m, j, -1, 0.0, nullptr, nullptr));
+        cudaEvent_t e0 = prof_mark(c);
         BSDE_TRY(launch_interface_right(*m.in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == d - 1 ? nullptr : m.B->at(j + 1),
                                         m.B->at(j), c->stream));
         c->launches++;
+        prof_span(c, bsde_ctx::P_INTERFACE, e0, prof_mark(c));
     }
     return 0;
 }
@@ -354,12 +408,14 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
         int it = 0;
         if (n_iter > 0) { BSDE_TRY(als_sweep(c, m)); it = 1; }     // also builds the assembly plans / workspaces
         if (it < n_iter) {
-            if (c->use_graph && n_iter - it >= 2) {
+            if (c->use_graph && !c->profile && n_iter - it >= 2) {
                 cudaGraph_t graph = nullptr;
                 cudaGraphExec_t exec = nullptr;
                 const int64_t before = c->launches;
                 BSDE_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                c->capturing = true;
                 const int rc = als_sweep(c, m);
+                c->capturing = false;
                 cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
                 if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
@@ -381,6 +437,7 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
         }
     }
     BSDE_TRY(train_download(c, T, cores_host));
+    prof_collect(c);
     if (info_host) {
         BSDE_CUDA_OK(cudaMemcpy(info_host, info, sizeof(int) * 4, cudaMemcpyDeviceToHost));
         if (info_host[3] == INT_MAX) info_host[3] = 0;
@@ -424,6 +481,7 @@ int bsde_ctx_destroy(bsde_ctx* c) {
     for (auto& kv : c->plans) asm_plan_free(kv.second);
     for (DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg})
         b->release();
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->own);
     delete c;
     return 0;
@@ -451,7 +509,34 @@ int bsde_ctx_launch_count(bsde_ctx* c, int64_t* out) {
 int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     BSDE_CHECK_CTX(c);
     if (name && !strcmp(name, "use_graph")) { c->use_graph = value; return 0; }
+    if (name && !strcmp(name, "profile")) {      // per-kernel-class event timing of eager launches; resets the counters
+        c->profile = value;
+        for (int k = 0; k < bsde_ctx::P_CLASSES; k++) { c->prof_ms[k] = 0.0; c->prof_n[k] = 0; }
+        return 0;
+    }
     return fail_msg(2, "unknown option '%s'", name ? name : "(null)");
+}
+
+int bsde_ctx_get_stat(bsde_ctx* c, const char* name, double* out) {
+    BSDE_CHECK_CTX(c);
+    if (!name || !out) return fail_msg(2, "bsde_ctx_get_stat: null argument");
+    static const char* cls[bsde_ctx::P_CLASSES] = {"assembly", "reduce", "allreduce", "solve", "interface"};
+    for (int k = 0; k < bsde_ctx::P_CLASSES; k++) {
+        const size_t n = strlen(cls[k]);
+        if (!strncmp(name, cls[k], n)) {
+            if (!strcmp(name + n, "_ms")) { *out = c->prof_ms[k]; return 0; }
+            if (!strcmp(name + n, "_n")) { *out = (double)c->prof_n[k]; return 0; }
+        }
+    }
+    if (!strcmp(name, "sm_count")) { *out = c->sm_count; return 0; }
+    if (!strcmp(name, "workspace_bytes")) {
+        double t = 0;
+        for (const DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg})
+            t += (double)b->cap;
+        *out = t;
+        return 0;
+    }
+    return fail_msg(2, "unknown stat '%s'", name);
 }
 
 int bsde_comm_unique_id(void* out128) {

@@ -54,13 +54,28 @@ struct AsmArgs {
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// One 8x8 output tile over the 32 staged samples: 8 DMMA.8x8x4, the B fragment formed as a product of two staged
+// factors.  `w` already includes the lane's sample slot (lane & 3); the offsets are in doubles.
+__device__ __forceinline__ void tile_pair(const double* __restrict__ w, unsigned long long ta, unsigned long long tb,
+                                          double (&ca)[2], double (&cb)[2]) {
+    const int ra = (int)(ta & 0xffffu), a1 = (int)((ta >> 16) & 0xffffu), a2 = (int)((ta >> 32) & 0xffffu);
+    const int rb = (int)(tb & 0xffffu), b1 = (int)((tb >> 16) & 0xffffu), b2 = (int)((tb >> 32) & 0xffffu);
+#pragma unroll
+    for (int step = 0; step < 8; step++) {
+        const double xa = w[ra + step * 4], pa = w[a1 + step * 4] * w[a2 + step * 4];
+        const double xb = w[rb + step * 4], pb = w[b1 + step * 4] * w[b2 + step * 4];
+        dmma884(ca[0], ca[1], xa, pa);
+        dmma884(cb[0], cb[1], xb, pb);
+    }
 }
 
 template <int NJ, int RB, int PB>
-__global__ void __launch_bounds__(kAsmThreads)
+__global__ void __launch_bounds__(kAsmThreads, (NJ >= 16 ? 4 : 6))
 k_assemble(AsmArgs a) {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,21 +83,16 @@ k_assemble(AsmArgs a) {
     const int group = blockIdx.y;
     const int64_t N = a.in.N;
 
-    // per-lane fragment sources for this warp's NJ tiles
-    int offr[NJ], off1[NJ], off2[NJ];
-    unsigned long long flagbits = 0ull;
-    {
-        const int g8 = lane >> 2;
-#pragma unroll
-        for (int jb = 0; jb < NJ; jb++) {
-            const int job = group * NJ + jb;
-            const uint16_t* t = a.tab + ((size_t)job * 8 + g8) * 3;
-            offr[jb] = (int)t[0] * kStride;
-            off1[jb] = (int)t[1] * kStride;
-            off2[jb] = (int)t[2] * kStride;
-            flagbits |= (unsigned long long)(a.flags[job] & 7) << (3 * jb);
-        }
+    // this group's tile table: per (tile, lane group) the staged-function offsets (doubles) of the A fragment row
+    // and of the two B fragment factors, packed 3 x 16 bit
+    unsigned long long* stab = reinterpret_cast<unsigned long long*>(sm + (size_t)kAsmWarps * a.warp_doubles);
+    for (int e = threadIdx.x; e < NJ * 8; e += kAsmThreads) {
+        const uint16_t* t = a.tab + ((size_t)(group * NJ) * 8 + e) * 3;
+        stab[e] = (unsigned long long)(t[0] * kStride) | ((unsigned long long)(t[1] * kStride) << 16) |
+                  ((unsigned long long)(t[2] * kStride) << 32);
     }
+    __syncthreads();
+    const unsigned long long* mytab = stab + (lane >> 2);
 
     double acc[NJ][2];
 #pragma unroll
@@ -148,21 +158,10 @@ k_assemble(AsmArgs a) {
                 if (m < a.in.p) ws[(a.fRow2 + m) * kStride + lane] = phi[m] * yv;
         }
         __syncwarp();
-        // ---------------- phase 2: DMMA over the staged 32 samples ----------------
-#pragma unroll 2
-        for (int step = 0; step < 8; step++) {
-            const int sl = step * 4 + (lane & 3);
-            double ar = 0.0, c1 = 0.0, c2 = 0.0, prod = 0.0;
+        // ---------------- phase 2: DMMA over the staged 32 samples, two independent tiles at a time ----------------
+        const double* w = ws + (lane & 3);
 #pragma unroll
-            for (int jb = 0; jb < NJ; jb++) {
-                const unsigned fl = (unsigned)(flagbits >> (3 * jb)) & 7u;
-                if (fl & 1u) ar = ws[offr[jb] + sl];
-                if (fl & 2u) c1 = ws[off1[jb] + sl];
-                if (fl & 4u) c2 = ws[off2[jb] + sl];
-                if (fl & 6u) prod = c1 * c2;
-                dmma884(acc[jb][0], acc[jb][1], ar, prod);
-            }
-        }
+        for (int jb = 0; jb < NJ; jb += 2) tile_pair(w, mytab[jb * 8], mytab[(jb + 1) * 8], acc[jb], acc[jb + 1]);
         __syncwarp();
     }
 
@@ -351,14 +350,14 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
     }
 
     const int warp_doubles = std::max(P.F * kStride, P.NJ * 64 + 1);
-    P.smem_bytes = (size_t)kAsmWarps * warp_doubles * sizeof(double);
+    P.smem_bytes = (size_t)kAsmWarps * warp_doubles * sizeof(double) + (size_t)P.NJ * 8 * sizeof(unsigned long long);
     if (P.smem_bytes > 200 * 1024) return fail_msg(2, "assembly: core shape (%d,%d,%d) needs %zu B of shared memory", rl, p, rr, P.smem_bytes);
     const int64_t nchunks = (N + 31) / 32;
     const int64_t want = (nchunks + kAsmWarps - 1) / kAsmWarps;
     int per_sm = 1;
     { const int rc = asm_blocks_per_sm(P, &per_sm); if (rc) return rc; }
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     P.grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count * per_sm));
 
     BSDE_CUDA_OK(cudaMalloc(&P.d_tab, tab.size() * sizeof(uint16_t)));
@@ -378,12 +377,12 @@ void asm_plan_free(AsmPlan& P) {
 }
 
 int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, const double* R, const double* y,
-                    double* partial, double* moments, cudaStream_t st) {
+                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid) {
     AsmArgs a;
     a.in = in; a.j = j; a.L = L; a.R = R; a.y = y;
     a.rl = P.rl; a.rr = P.rr; a.mono = P.mono; a.nB = P.nB;
     a.F = P.F; a.fLL = P.fLL; a.fRR = P.fRR; a.fRow1 = P.fRow1; a.fL = P.fL; a.fR = P.fR; a.fRow2 = P.fRow2;
-    a.warp_doubles = (int)(P.smem_bytes / sizeof(double) / kAsmWarps);
+    a.warp_doubles = (int)((P.smem_bytes - (size_t)P.NJ * 8 * sizeof(unsigned long long)) / sizeof(double) / kAsmWarps);
     a.tab = P.d_tab; a.flags = P.d_flags;
     a.partial = partial; a.partial_stride = P.partial_stride;
     int rc;
@@ -391,6 +390,7 @@ int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, 
     else if (P.NJ == 8) rc = launch_nj<8>(P, a, st);
     else rc = launch_nj<16>(P, a, st);
     if (rc) return rc;
+    if (mid) BSDE_CUDA_OK(cudaEventRecord(mid, st));
     k_moment_reduce<<<(P.n_mom + 31) / 32, 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride, P.d_gather, P.n_mom, moments);
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -36,7 +36,7 @@ __device__ __forceinline__ void two_prod(double a, double b, double& p, double& 
 }
 __device__ __forceinline__ void fast_two_sum(double a, double b, double& s, double& e) {
     s = __dadd_rn(a, b);
-    e = __dadd_rn(b, __dadd_rn(s, -a));
+    e = __dadd_rn(b, -__dadd_rn(s, -a));      // b - (s - a)
 }
 
 // Monomials x^0..x^{PB-1}, each rounded once from a double-double running product, so that they agree

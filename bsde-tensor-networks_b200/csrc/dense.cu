@@ -18,7 +18,7 @@ namespace bsde {
 
 namespace {
 
-constexpr int kDenseThreads = 256;
+constexpr int kDenseThreads = 1024;   // 32 warps: one Jacobi pair per warp for n = 64; the Cholesky path uses 8 of them
 
 __device__ __forceinline__ int pair_index(int a, int b, int r) {   // a <= b < r, row-major upper triangle
     return a * r - (a * (a - 1)) / 2 + (b - a);
@@ -130,58 +130,68 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
     }
 }
 
-// Equilibrated Cholesky of [A b; b^T .] (lower triangle, in place).  Returns false (uniformly) if a pivot shows
-// that A is too close to lstsq's truncation threshold for "exact solve == lstsq" to be guaranteed.
-__device__ bool cholesky_solve(SolveScratch& S, int n, double* xout) {
+// Named barrier for the first `count` threads of the CTA (the fast path runs on 8 of the 32 warps).
+__device__ __forceinline__ void bar_sub(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
+
+constexpr int kCholThreads = 256;
+constexpr double kGateSafety = 100.0;
+
+// Fast path of 'lstsq', executed by threads 0..255: equilibrated Cholesky of A with two right-hand sides carried
+// through the factorisation as extra rows — b (row n) and a fixed +-1 probe vector e (row n+1).  The probe gives
+// sigma_min(A) <= |e| / |A^-1 e|; with sigma_max(A) <= trace(A) the test
+//        (|e| / |A^-1 e|) / trace(A)  >  kGateSafety * eps * n
+// certifies that numpy.linalg.lstsq(rcond=None) (cutoff eps*n*sigma_max) would not have truncated any singular
+// value, i.e. that the exact solve IS the lstsq answer.  Anything else (non-positive pivot, failed test) returns
+// false and the caller takes the SVD path, which reproduces the truncation rule literally.
+__device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_red) {
     const int ld = n + 1;
     double* A = S.A;
-    __shared__ double s_min, s_dmin, s_dmax;
-    __shared__ int s_bad;
-    if (threadIdx.x == 0) {
-        double dmin = DBL_MAX, dmax = 0.0;
+    const int tid = threadIdx.x;
+    // s_red: [0] trace, [1] bad flag, [2] |z|^2
+    if (tid < 32) {
+        double tr = 0.0;
         int bad = 0;
-        for (int i = 0; i < n; i++) {
+        for (int i = tid; i < n; i += 32) {
             const double d = A[i * ld + i];
             if (!(d > 0.0) || !isfinite(d)) bad = 1;
-            dmin = fmin(dmin, d);
-            dmax = fmax(dmax, d);
+            tr += d;
         }
-        s_dmin = dmin; s_dmax = dmax; s_bad = bad; s_min = 1.0;
+        tr = warp_sum(tr);
+        bad = __any_sync(0xffffffffu, bad);
+        if (tid == 0) { s_red[0] = tr; s_red[1] = bad ? 1.0 : 0.0; }
     }
-    __syncthreads();
-    if (s_bad) return false;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) S.sc[i] = 1.0 / sqrt(A[i * ld + i]);
-    __syncthreads();
-    // scale lower triangle and the b row (row n)
-    for (int e = threadIdx.x; e < (n + 1) * n; e += blockDim.x) {
-        const int i = e / n, j = e % n;
-        if (i == n) A[n * ld + j] = S.bvec[j] * S.sc[j];
+    bar_sub(kCholThreads);
+    if (s_red[1] != 0.0) return false;
+    for (int i = tid; i < n; i += kCholThreads) S.sc[i] = 1.0 / sqrt(A[i * ld + i]);
+    bar_sub(kCholThreads);
+    // scale the lower triangle; rows n, n+1 = equilibrated right-hand sides
+    for (int e = tid; e < (n + 2) * n; e += kCholThreads) {
+        const int i = e / n, j = e - i * n;
+        if (i == n) A[i * ld + j] = S.bvec[j] * S.sc[j];
+        else if (i == n + 1) A[i * ld + j] = ((((unsigned)j * 2654435761u) >> 7) & 1u ? 1.0 : -1.0) * S.sc[j];
         else if (j <= i) A[i * ld + j] *= S.sc[i] * S.sc[j];
     }
-    __syncthreads();
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    const double thresh = (double)n * (double)n * 1e-12;
+    bar_sub(kCholThreads);
+    const int ty = tid >> 4, tx = tid & 15;
     for (int k = 0; k < n; k++) {
         const double piv = A[k * ld + k];
         if (!(piv > 0.0)) return false;                       // uniform: every thread reads the same value
-        if (threadIdx.x == 0 && piv < s_min) s_min = piv;
-        const double inv = 1.0 / sqrt(piv);
-        __syncthreads();
-        for (int i = k + 1 + threadIdx.x; i <= n; i += blockDim.x) A[i * ld + k] *= inv;
-        if (threadIdx.x == 0) A[k * ld + k] = inv;            // keep the reciprocal of the diagonal of the factor
-        __syncthreads();
-        for (int i = k + 1 + ty; i <= n; i += 16) {
+        const double inv = rsqrt(piv);
+        bar_sub(kCholThreads);
+        for (int i = k + 1 + tid; i <= n + 1; i += kCholThreads) A[i * ld + k] *= inv;
+        if (tid == 0) A[k * ld + k] = inv;                    // keep the reciprocal of the factor's diagonal
+        bar_sub(kCholThreads);
+        for (int i = k + 1 + ty; i <= n + 1; i += 16) {
             const double lik = A[i * ld + k];
             const int jmax = (i < n) ? i : n - 1;
             for (int j = k + 1 + tx; j <= jmax; j += 16) A[i * ld + j] = fma(-lik, A[j * ld + k], A[i * ld + j]);
         }
-        __syncthreads();
+        bar_sub(kCholThreads);
     }
-    if (!(s_min * (s_dmin / s_dmax) > thresh)) return false;
-    // back substitution  L^T xs = z  (z = row n of the factor), one warp; diag holds reciprocals
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        double* z = A + n * ld;
+    // back substitution L^T x = z for both right-hand sides: warp 0 -> b, warp 1 -> probe
+    if (tid < 64) {
+        const int lane = tid & 31;
+        double* z = A + (n + (tid >> 5)) * ld;
         for (int k = n - 1; k >= 0; k--) {
             const double xk = z[k] * A[k * ld + k];
             __syncwarp();
@@ -189,10 +199,20 @@ __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout) {
             for (int i = lane; i < k; i += 32) z[i] = fma(-A[k * ld + i], xk, z[i]);
             __syncwarp();
         }
-        for (int i = lane; i < n; i += 32) xout[i] = z[i] * S.sc[i];
+        if (tid < 32) {
+            for (int i = lane; i < n; i += 32) xout[i] = z[i] * S.sc[i];
+        } else {
+            double zz = 0.0;
+            for (int i = lane; i < n; i += 32) { const double v = z[i] * S.sc[i]; zz = fma(v, v, zz); }
+            zz = warp_sum(zz);
+            if (lane == 0) s_red[2] = zz;
+        }
     }
-    __syncthreads();
-    return true;
+    bar_sub(kCholThreads);
+    const double zz = s_red[2];
+    if (!isfinite(zz) || !(zz > 0.0)) return false;
+    const double sigma_min_bound = sqrt((double)n / zz);
+    return sigma_min_bound / s_red[0] > kGateSafety * DBL_EPSILON * (double)n;
 }
 
 // One-sided (Hestenes) Jacobi SVD of the n x n matrix held column-major in G; V accumulates the right vectors.
@@ -301,7 +321,7 @@ __device__ void lu_solve(SolveScratch& S, int n, double* xout) {
         __syncthreads();
         const double inv = 1.0 / A[k * ld + k];
         __syncthreads();
-        for (int i = k + 1 + (threadIdx.x >> 4); i < n; i += 16) {
+        for (int i = k + 1 + (threadIdx.x >> 4); i < n; i += (blockDim.x >> 4)) {
             const double f = A[i * ld + k] * inv;
             for (int j = k + 1 + (threadIdx.x & 15); j <= n; j += 16) A[i * ld + j] = fma(-f, A[k * ld + j], A[i * ld + j]);
         }
@@ -326,9 +346,9 @@ k_micro_solve(MicroSolveArgs a) {
     const int n = a.rl * a.p * a.rr;
     const int ld = n + 1;
     SolveScratch S;
-    S.A = sm;                                   // (n+1)^2 : augmented normal equations / Jacobi G / QR work matrix
+    S.A = sm;                                   // (n+2) x (n+1): augmented normal equations / Jacobi G / QR work matrix
     S.G = sm;
-    S.V = sm + (size_t)(n + 1) * (n + 1);       // n^2     : Jacobi right vectors
+    S.V = sm + (size_t)(n + 2) * (n + 1);       // n^2     : Jacobi right vectors
     S.x = S.V + (size_t)n * n;                  // n
     S.sc = S.x + n;                             // n
     S.bvec = S.sc + n;                          // n
@@ -337,7 +357,8 @@ k_micro_solve(MicroSolveArgs a) {
     double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
     double* tau = qrR + kMaxR * kMaxR;          // kMaxR
     double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
-    __shared__ int s_path, s_rank;
+    __shared__ int s_path, s_rank, s_ok;
+    __shared__ double s_red[4];
 
     expand_normal_equations(a, S.A, ld, S.bvec);
     __syncthreads();
@@ -347,10 +368,12 @@ k_micro_solve(MicroSolveArgs a) {
     }
     __syncthreads();
     if (a.solver == SOLVER_LSTSQ) {
-        const bool ok = cholesky_solve(S, n, S.x);
-        if (threadIdx.x == 0) { s_path = ok ? 0 : 1; s_rank = n; }
-        if (!ok) {
-            __syncthreads();
+        if (threadIdx.x < kCholThreads) {
+            const bool ok = cholesky_solve(S, n, S.x, s_red);
+            if (threadIdx.x == 0) { s_ok = ok ? 1 : 0; s_path = ok ? 0 : 1; s_rank = n; }
+        }
+        __syncthreads();
+        if (!s_ok) {
             // rebuild A (column-major == row-major, A is symmetric) with ld = n for the Jacobi path
             expand_normal_equations(a, S.G, n, S.bvec);
             __syncthreads();
@@ -491,7 +514,7 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st) {
     if (a.direction > 0 && a.rl * a.p < a.rr) return fail_msg(2, "micro_solve: left QR needs r_j*p >= r_{j+1} (%d*%d < %d)", a.rl, a.p, a.rr);
     if (a.direction < 0 && a.p * a.rr < a.rl) return fail_msg(2, "micro_solve: right QR needs p*r_{j+1} >= r_j (%d*%d < %d)", a.p, a.rr, a.rl);
     // keep in sync with the layout at the top of k_micro_solve
-    const size_t doubles = (size_t)(n + 1) * (n + 1) + (size_t)n * n + 4 * (size_t)n + kMaxR * kMaxP * kMaxR +
+    const size_t doubles = (size_t)(n + 2) * (n + 1) + (size_t)n * n + 4 * (size_t)n + kMaxR * kMaxP * kMaxR +
                            kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16;
     const size_t bytes = doubles * sizeof(double);
     static bool attr_set = false;

@@ -43,7 +43,7 @@ void asm_plan_free(AsmPlan& plan);
 // Launches the assembly kernel and the partial reduction; `moments` (n_mom doubles, device) receives
 // [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y].
 int launch_assembly(const AsmPlan& plan, const Inputs& in, int j, const double* L, const double* R, const double* y,
-                    double* partial, double* moments, cudaStream_t st);
+                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid = nullptr);
 
 // ---- dense.cu ------------------------------------------------------------------------------------
 enum SolverId : int { SOLVER_LSTSQ = 0, SOLVER_LU = 1, SOLVER_QR = 2, SOLVER_SOLVE = 3 };

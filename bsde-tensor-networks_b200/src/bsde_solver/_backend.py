@@ -71,11 +71,26 @@ class Backend:
         check(self.lib.bsde_ctx_create(self.device, C.byref(ctx)))
         self.ctx = ctx
         self.rank, self.world = 0, 1
+        # The library works on its own stream (CUDA graphs cannot be captured on the legacy default stream that
+        # torch uses by default).  Every call is fenced against torch's current stream on both sides, so tensors
+        # produced by torch before the call and tensors read by torch after it are ordered correctly.
+        self.stream = torch.cuda.Stream(device=self.tdev)
+        check(self.lib.bsde_ctx_set_stream(self.ctx, C.c_void_p(self.stream.cuda_stream)))
 
     # ---- plumbing ----------------------------------------------------------------------------------------
     def _enter(self):
-        torch = _torch()
-        check(self.lib.bsde_ctx_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)))
+        self.stream.wait_stream(_torch().cuda.current_stream(self.tdev))
+
+    def _exit(self):
+        _torch().cuda.current_stream(self.tdev).wait_stream(self.stream)
+
+    def _call(self, fn, *args):
+        """One C-ABI call on the library's stream, fenced against torch's current stream on both sides."""
+        self._enter()
+        try:
+            check(fn(self.ctx, *args))
+        finally:
+            self._exit()
 
     def empty(self, *shape):
         torch = _torch()
@@ -98,6 +113,11 @@ class Backend:
     def set_option(self, name, value):
         check(self.lib.bsde_ctx_set_option(self.ctx, name.encode(), int(value)))
 
+    def get_stat(self, name):
+        out = C.c_double()
+        check(self.lib.bsde_ctx_get_stat(self.ctx, name.encode(), C.byref(out)))
+        return out.value
+
     def init_distributed(self):
         """Sample-sharded data parallelism: bootstrap the library's NCCL communicator over torch.distributed."""
         torch = _torch()
@@ -119,51 +139,45 @@ class Backend:
 
     # ---- the hot path ------------------------------------------------------------------------------------
     def fit_als(self, inp: DeviceInputs, y, n_iter, ranks, solver_id, cores_flat):
-        self._enter()
         ranks = _i32(ranks)
         info = np.zeros(4, dtype=np.int32)
-        check(self.lib.bsde_fit_als(self.ctx, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef), _ptr(y),
-                                    int(n_iter), _ptr(ranks), int(solver_id), _ptr(cores_flat), _ptr(info)))
+        self._call(self.lib.bsde_fit_als, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef), _ptr(y),
+                                    int(n_iter), _ptr(ranks), int(solver_id), _ptr(cores_flat), _ptr(info))
         return info
 
     def fit_als_host(self, kind, d, p, N, inputs_host, coef, y_host, n_iter, ranks, solver_id, cores_flat):
-        self._enter()
         ranks = _i32(ranks)
         info = np.zeros(4, dtype=np.int32)
         coef = None if coef is None else _f64(coef)
-        check(self.lib.bsde_fit_als_host(self.ctx, int(kind), int(d), int(p), int(N), _ptr(inputs_host), _ptr(coef),
+        self._call(self.lib.bsde_fit_als_host, int(kind), int(d), int(p), int(N), _ptr(inputs_host), _ptr(coef),
                                          _ptr(y_host), int(n_iter), _ptr(ranks), int(solver_id), _ptr(cores_flat),
-                                         _ptr(info)))
+                                         _ptr(info))
         return info
 
     def fit_salsa(self, inp: DeviceInputs, y, n_iter, ranks, init_ranks, omega, freq_omega, min_sv, max_rank, solver_id,
                   do_reg, cores_buf):
-        self._enter()
         state = np.zeros(8, dtype=np.float64)
-        check(self.lib.bsde_fit_salsa(self.ctx, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef), _ptr(y),
+        self._call(self.lib.bsde_fit_salsa, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef), _ptr(y),
                                       int(n_iter), _ptr(ranks), _ptr(_i32(init_ranks)), float(omega), float(freq_omega),
                                       float(min_sv), int(max_rank), int(solver_id), int(bool(do_reg)), _ptr(cores_buf),
-                                      cores_buf.size, _ptr(state)))
+                                      cores_buf.size, _ptr(state))
         return state
 
     def tt_eval(self, inp: DeviceInputs, ranks, cores_flat, out=None):
-        self._enter()
         out = self.empty(inp.N) if out is None else out
-        check(self.lib.bsde_tt_eval(self.ctx, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef),
-                                    _ptr(_i32(ranks)), _ptr(_f64(cores_flat)), _ptr(out)))
+        self._call(self.lib.bsde_tt_eval, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef),
+                                    _ptr(_i32(ranks)), _ptr(_f64(cores_flat)), _ptr(out))
         return out
 
     def tt_grad(self, inp: DeviceInputs, ranks, cores_flat, out=None):
-        self._enter()
         out = self.empty(inp.d, inp.N) if out is None else out
-        check(self.lib.bsde_tt_grad(self.ctx, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.ddata),
-                                    _ptr(inp.coef), _ptr(_i32(ranks)), _ptr(_f64(cores_flat)), _ptr(out)))
+        self._call(self.lib.bsde_tt_grad, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.ddata),
+                                    _ptr(inp.coef), _ptr(_i32(ranks)), _ptr(_f64(cores_flat)), _ptr(out))
         return out
 
     # ---- paths, targets ----------------------------------------------------------------------------------
     def paths_simulate(self, model_id, params, x0, N, steps, T, seed=0, sample_offset=0, xi=None, keep_xi=True):
         """x [steps+1][d][N] (and xi in the same layout).  `xi` given => replay of host-supplied increments."""
-        self._enter()
         x0 = _f64(x0)
         d = x0.shape[0]
         x = self.empty(steps + 1, d, N)
@@ -172,70 +186,62 @@ class Backend:
             xi = self.to_device(xi)
         elif keep_xi:
             xi = self.empty(steps + 1, d, N)
-        check(self.lib.bsde_paths_simulate(self.ctx, int(model_id), _ptr(_f64(params)), d, int(N), int(steps), float(T),
-                                           _ptr(x0), int(seed), int(sample_offset), int(replay), _ptr(xi), _ptr(x)))
+        self._call(self.lib.bsde_paths_simulate, int(model_id), _ptr(_f64(params)), d, int(N), int(steps), float(T),
+                                           _ptr(x0), int(seed), int(sample_offset), int(replay), _ptr(xi), _ptr(x))
         return x, xi
 
     def terminal(self, model_id, params, x):
-        self._enter()
         d, N = x.shape
         out = self.empty(N)
-        check(self.lib.bsde_terminal(self.ctx, int(model_id), _ptr(_f64(params)), d, N, _ptr(x), _ptr(out)))
+        self._call(self.lib.bsde_terminal, int(model_id), _ptr(_f64(params)), d, N, _ptr(x), _ptr(out))
         return out
 
     def target(self, model_id, params, x, y, y_next, grad, xi, dt, apply_sigma, out=None):
-        self._enter()
         d, N = x.shape
         out = self.empty(N) if out is None else out
-        check(self.lib.bsde_target(self.ctx, int(model_id), _ptr(_f64(params)), d, N, _ptr(x), _ptr(y), _ptr(y_next),
-                                   _ptr(grad), _ptr(xi), float(dt), int(bool(apply_sigma)), _ptr(out)))
+        self._call(self.lib.bsde_target, int(model_id), _ptr(_f64(params)), d, N, _ptr(x), _ptr(y), _ptr(y_next),
+                                   _ptr(grad), _ptr(xi), float(dt), int(bool(apply_sigma)), _ptr(out))
         return out
 
     def mean(self, v):
-        self._enter()
         out = C.c_double()
-        check(self.lib.bsde_mean(self.ctx, _ptr(v), int(v.numel()), C.byref(out)))
+        self._call(self.lib.bsde_mean, _ptr(v), int(v.numel()), C.byref(out))
         return out.value
 
     def transpose(self, src, rows, cols):
-        self._enter()
         dst = self.empty(cols, rows)
-        check(self.lib.bsde_transpose(self.ctx, _ptr(src), int(rows), int(cols), _ptr(dst)))
+        self._call(self.lib.bsde_transpose, _ptr(src), int(rows), int(cols), _ptr(dst))
         return dst
 
     # ---- verification hooks ------------------------------------------------------------------------------
     def normal_eq(self, inp: DeviceInputs, y, ranks, cores_flat, j):
-        self._enter()
         ranks = _i32(ranks)
         n = int(ranks[j]) * inp.p * int(ranks[j + 1])
         A = np.zeros((n, n))
         b = np.zeros(n)
-        check(self.lib.bsde_normal_eq(self.ctx, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef), _ptr(y),
-                                      _ptr(ranks), _ptr(_f64(cores_flat)), int(j), _ptr(A), _ptr(b)))
+        self._call(self.lib.bsde_normal_eq, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.coef), _ptr(y),
+                                      _ptr(ranks), _ptr(_f64(cores_flat)), int(j), _ptr(A), _ptr(b))
         return A, b
 
     def solve(self, A, b, solver_id):
-        self._enter()
         A, b = _f64(A), _f64(b)
         n = b.shape[0]
         x = np.zeros(n)
         info = np.zeros(4, dtype=np.int32)
-        check(self.lib.bsde_solve(self.ctx, n, _ptr(A), _ptr(b), int(solver_id), _ptr(x), _ptr(info)))
+        self._call(self.lib.bsde_solve, n, _ptr(A), _ptr(b), int(solver_id), _ptr(x), _ptr(info))
         return x, info
 
     def orthonormalize(self, p, ranks, cores_flat, mode, start, stop):
-        self._enter()
         ranks = _i32(ranks)
-        check(self.lib.bsde_orthonormalize(self.ctx, len(ranks) - 1, int(p), _ptr(ranks), _ptr(cores_flat), int(mode),
-                                           int(start), int(stop)))
+        self._call(self.lib.bsde_orthonormalize, len(ranks) - 1, int(p), _ptr(ranks), _ptr(cores_flat), int(mode),
+                                           int(start), int(stop))
         return cores_flat
 
     def basis_eval(self, kind, p, x, coef, deriv):
-        self._enter()
         N = int(x.numel())
         out = self.empty(p, N)
         coef = None if coef is None else _f64(coef)
-        check(self.lib.bsde_basis_eval(self.ctx, int(kind), int(p), N, _ptr(x), _ptr(coef), int(deriv), _ptr(out)))
+        self._call(self.lib.bsde_basis_eval, int(kind), int(p), N, _ptr(x), _ptr(coef), int(deriv), _ptr(out))
         return out
 
 

@@ -29,6 +29,7 @@ SIGNATURES = {
     "bsde_ctx_sync": [_vp],
     "bsde_ctx_launch_count": [_vp, C.POINTER(_i64)],
     "bsde_ctx_set_option": [_vp, C.c_char_p, _i64],
+    "bsde_ctx_get_stat": [_vp, C.c_char_p, C.POINTER(C.c_double)],
     "bsde_comm_unique_id": [_vp],
     "bsde_comm_init": [_vp, _vp, C.c_int, C.c_int],
     "bsde_malloc": [_vp, _i64, C.POINTER(_vp)],

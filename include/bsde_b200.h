@@ -61,8 +61,12 @@ BSDE_API int bsde_ctx_set_stream(bsde_ctx* ctx, void* cuda_stream);
 BSDE_API int bsde_ctx_sync(bsde_ctx* ctx);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 BSDE_API int bsde_ctx_launch_count(bsde_ctx* ctx, int64_t* out);
-/* use CUDA graphs for the ALS sweep (default 1) */
+/* options: "use_graph" (CUDA graph per ALS sweep, default 1); "profile" (1 = time every eager kernel launch with
+ * CUDA events by class and disable graphs; setting it resets the counters) */
 BSDE_API int bsde_ctx_set_option(bsde_ctx* ctx, const char* name, int64_t value);
+/* stats: "<class>_ms" / "<class>_n" for class in assembly, reduce, allreduce, solve, interface (device time and
+ * launch count accumulated while "profile" is on); "sm_count"; "workspace_bytes" */
+BSDE_API int bsde_ctx_get_stat(bsde_ctx* ctx, const char* name, double* out);
 
 /* sample-sharded data parallelism: one process per GPU, NCCL all-reduce of the per-core moments.
  * bsde_comm_unique_id fills 128 bytes on rank 0; broadcast them (torch.distributed / MPI) and call bsde_comm_init. */
