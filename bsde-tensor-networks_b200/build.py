@@ -27,7 +27,9 @@ def _newer(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=OUT, objdir=OBJ):
+    """defines / out / objdir: alternative builds of kernel variants for A/B measurements (bench only)."""
+    OBJ = objdir
     os.makedirs(OBJ, exist_ok=True)
     sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
@@ -36,7 +38,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         if not force and _newer(obj, [os.path.join(CSRC, src)] + hdrs):
             return obj
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -46,13 +48,17 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(sources)) as ex:
         objs = list(ex.map(compile_one, sources))
-    if force or not _newer(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ldl"]
+    if force or not _newer(out, objs):
+        cmd = [NVCC, "-shared", "-o", out] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    if defs:      # variant build: python build.py -DNAME=VALUE ... -> libbsde_b200_variant.so
+        print(build(force=True, defines=defs, out=os.path.join(HERE, "libbsde_b200_variant.so"), objdir=os.path.join(HERE, "build_variant")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -96,6 +96,7 @@ struct bsde_ctx {
     int64_t use_graph = 1;
     DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg;
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
+    int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     // per-kernel-class device timing (option "profile"): event pairs recorded around eager launches
@@ -136,7 +137,7 @@ int get_plan(bsde_ctx* c, int rl, int p, int rr, int mono, int64_t N, const AsmP
             c->plans.clear();
         }
         AsmPlan P;
-        BSDE_TRY(asm_plan_build(P, rl, p, rr, mono, N, c->sm_count));
+        BSDE_TRY(asm_plan_build(P, rl, p, rr, mono, N, c->sm_count, (int)c->asm_generic));
         it = c->plans.emplace(key, std::move(P)).first;
     }
     *out = &it->second;
@@ -509,6 +510,12 @@ int bsde_ctx_launch_count(bsde_ctx* c, int64_t* out) {
 int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     BSDE_CHECK_CTX(c);
     if (name && !strcmp(name, "use_graph")) { c->use_graph = value; return 0; }
+    if (name && !strcmp(name, "asm_generic")) {
+        c->asm_generic = value;
+        for (auto& kv : c->plans) asm_plan_free(kv.second);
+        c->plans.clear();
+        return 0;
+    }
     if (name && !strcmp(name, "profile")) {      // per-kernel-class event timing of eager launches; resets the counters
         c->profile = value;
         for (int k = 0; k < bsde_ctx::P_CLASSES; k++) { c->prof_ms[k] = 0.0; c->prof_n[k] = 0; }

@@ -3,8 +3,8 @@
 //  V[s,(a,m,b)] = L_j[s,a] phi_j[s,m] R_j[s,b]).
 //
 // B200 facts this kernel is built on (bench/micro/fp64_peak.cu, measured): FP64 DMMA and DFMA issue at the same
-// rate (37 TFLOP/s) and share one pipe, and every f64 mma.sync shape is lowered to DMMA.8x8x4.  So the cost of
-// assembly is the number of FP64-pipe slots, and the plain V^T V product (n^2 FMAs / sample, or n(n+1)/2 on
+// rate (37 TFLOP/s) and every f64 mma.sync shape is lowered to DMMA.8x8x4 (16 cycles per SM sub-partition).  So the
+// cost of assembly is the number of DMMA slots, and the plain V^T V product (n^2 FMAs / sample, or n(n+1)/2 on
 // symmetric tiles) wastes most of them: V is a Kronecker product, hence
 //
 //   A[(a,m,b),(a',m',b')] = sum_s (L_a L_a')(phi_m phi_m')(R_b R_b')
@@ -16,13 +16,22 @@
 //   M2[m][a][b]           = sum_s (phi_m y)(s) * L_a(s) * R_b(s)           (= V^T y)
 //   yy                    = sum_s y_s^2
 //
-// (r=p=4: 700 + 64 + 1 numbers instead of 2080 + 64 + 1) as two skinny GEMMs over the sample axis on the
-// DMMA pipe: rows = basis-pair functions (one 8-row tile when 2p-1 <= 8), columns = LL (x) RR products.
+// (r=p=4: 700 + 64 + 1 numbers instead of 2080 + 64 + 1) as skinny GEMMs over the sample axis on the DMMA pipe.
 // The solve kernel (dense.cu) expands the moments into A and b.
 //
 // Execution: each warp owns 32 consecutive samples per iteration.  Phase 1 (lane = sample, coalesced loads)
 // evaluates the basis and stages the per-sample factor functions in shared memory; phase 2 runs 8 k-steps of
-// DMMA.8x8x4 (4 samples each) over all tiles, building each B fragment as one product of two staged factors.
+// DMMA.8x8x4 (4 samples each) over all output tiles.  Two phase-2 variants:
+//
+//   k_assemble_rb  register-blocked:  rows = (beta, lambda) pairs, columns = rho.  Per k-step every A fragment
+//                  (a product of two staged factors) is used for all column tiles and every B fragment for all row
+//                  tiles, so shared memory supplies ~2.4 wavefronts per DMMA and the kernel is DMMA-bound.
+//                  Instantiated for a few tile-count classes; shapes are padded up to the next class.
+//   k_assemble     generic, table driven:  rows = beta, columns = (lambda, rho) pairs, one independent fragment
+//                  triple per tile.  Fewer tiles (15 instead of 20 at r=p=4) but ~5 shared-memory wavefronts per
+//                  DMMA, which makes it LSU-bound (ncu: 82 % of the shared-memory pipe, DMMA pipe 52 %).
+//                  Fallback for shapes outside the register-blocked classes.
+//
 // Warps never synchronise with each other until the final fixed-order reduction, so results are bitwise
 // reproducible for a fixed launch shape.
 #include "common.cuh"
@@ -47,30 +56,249 @@ struct AsmArgs {
     int rl, rr, mono, nB;
     int F, fLL, fRR, fRow1, fL, fR, fRow2;
     int warp_doubles;            // shared-memory doubles per warp
-    const uint16_t* tab;
-    const uint8_t* flags;
+    const uint16_t* tab;         // generic: [tiles][8][3]; register-blocked: see asm_plan_build
+    int tab_entries;             // register-blocked: uint16 entries to copy into shared memory
     double* partial;
     int64_t partial_stride;
 };
 
+// volatile: keeps the DMMAs of one k-step together in program order (independent accumulators back to back)
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
 }
 
-// One 8x8 output tile over the 32 staged samples: 8 DMMA.8x8x4, the B fragment formed as a product of two staged
-// factors.  `w` already includes the lane's sample slot (lane & 3); the offsets are in doubles.
-__device__ __forceinline__ void tile_pair(const double* __restrict__ w, unsigned long long ta, unsigned long long tb,
-                                          double (&ca)[2], double (&cb)[2]) {
-    const int ra = (int)(ta & 0xffffu), a1 = (int)((ta >> 16) & 0xffffu), a2 = (int)((ta >> 32) & 0xffffu);
-    const int rb = (int)(tb & 0xffffu), b1 = (int)((tb >> 16) & 0xffffu), b2 = (int)((tb >> 32) & 0xffffu);
+// ---- phase 1: lane = sample ----
+// The raw per-sample inputs of the NEXT chunk are fetched into registers before phase 2 of the current one, so the
+// DRAM latency is hidden behind the DMMA work of the same warp (ncu: long_scoreboard was 20 % of the stalls).
+template <int RB, int PB>
+struct RawSample {
+    double L[RB], R[RB], y, vm;
+    double xb[PB];      // xb[0] = x (fused bases) or the p explicit basis values
+};
+
+template <int RB, int PB>
+__device__ __forceinline__ void load_raw(const AsmArgs& a, int lane, int64_t chunk, int64_t nchunks, RawSample<RB, PB>& r) {
+    const int64_t N = a.in.N;
+    if (chunk >= nchunks) chunk = nchunks - 1;            // past the end: a harmless re-read, never staged
+    const int64_t s = chunk * 32 + lane;
+    const bool valid = s < N;
+    const int64_t sc = valid ? s : N - 1;
+    r.vm = valid ? 1.0 : 0.0;
 #pragma unroll
-    for (int step = 0; step < 8; step++) {
-        const double xa = w[ra + step * 4], pa = w[a1 + step * 4] * w[a2 + step * 4];
-        const double xb = w[rb + step * 4], pb = w[b1 + step * 4] * w[b2 + step * 4];
-        dmma884(ca[0], ca[1], xa, pa);
-        dmma884(cb[0], cb[1], xb, pb);
+    for (int q = 0; q < RB; q++) {
+        r.L[q] = (q < a.rl) ? (a.L ? a.L[(int64_t)q * N + sc] : 1.0) : 0.0;
+        r.R[q] = (q < a.rr) ? (a.R ? a.R[(int64_t)q * N + sc] : 1.0) : 0.0;
+    }
+    r.y = a.y[sc];
+    if (a.in.kind == BASIS_PHI) {
+        const double* src = a.in.data + ((int64_t)a.j * a.in.p) * N + sc;
+#pragma unroll
+        for (int m = 0; m < PB; m++) r.xb[m] = (m < a.in.p) ? src[(int64_t)m * N] : 0.0;
+    } else {
+        r.xb[0] = a.in.data[(int64_t)a.j * N + sc];
+    }
+}
+
+// Stages function 0 = ZERO, LL pairs, RR pairs, basis rows, L, R, phi*y for the 32 samples of one chunk.
+template <int RB, int PB>
+__device__ __forceinline__ double stage_functions(const AsmArgs& a, double* __restrict__ ws, int lane, const RawSample<RB, PB>& r) {
+    const double vm = r.vm;
+    const double yv = r.y * vm;
+    ws[lane] = 0.0;
+    {
+        int idx = a.fLL;
+#pragma unroll
+        for (int q = 0; q < RB; q++)
+#pragma unroll
+            for (int q2 = q; q2 < RB; q2++)
+                if (q < a.rl && q2 < a.rl) { ws[idx * kStride + lane] = r.L[q] * r.L[q2]; idx++; }
+        idx = a.fRR;
+#pragma unroll
+        for (int q = 0; q < RB; q++)
+#pragma unroll
+            for (int q2 = q; q2 < RB; q2++)
+                if (q < a.rr && q2 < a.rr) { ws[idx * kStride + lane] = r.R[q] * r.R[q2]; idx++; }
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            if (q < a.rl) ws[(a.fL + q) * kStride + lane] = r.L[q];
+            if (q < a.rr) ws[(a.fR + q) * kStride + lane] = r.R[q];
+        }
+    }
+    if (a.mono) {
+        const double x = r.xb[0];
+        double pw = vm;
+#pragma unroll
+        for (int k = 0; k < 2 * PB - 1; k++) {
+            if (k < a.nB) ws[(a.fRow1 + k) * kStride + lane] = pw;
+            if (k < a.in.p) ws[(a.fRow2 + k) * kStride + lane] = pw * yv;
+            pw *= x;
+        }
+    } else {
+        double phi[PB];
+        if (a.in.kind == BASIS_PHI) {
+#pragma unroll
+            for (int m = 0; m < PB; m++) phi[m] = r.xb[m];
+        } else {
+            basis_from_x<PB>(a.in, r.xb[0], 0, phi);
+        }
+        int idx = a.fRow1;
+#pragma unroll
+        for (int m = 0; m < PB; m++)
+#pragma unroll
+            for (int m2 = m; m2 < PB; m2++)
+                if (m < a.in.p && m2 < a.in.p) { ws[idx * kStride + lane] = vm * phi[m] * phi[m2]; idx++; }
+#pragma unroll
+        for (int m = 0; m < PB; m++)
+            if (m < a.in.p) ws[(a.fRow2 + m) * kStride + lane] = phi[m] * yv;
+    }
+    return yv * yv;
+}
+
+// ---- epilogue: fixed-order sum of the warps' tiles, one partial row per CTA ----
+template <int NT>
+__device__ __forceinline__ void write_partials(const AsmArgs& a, double* sm, double* ws, const double (&acc)[NT][2],
+                                               double accyy, int lane, int tile_base, bool write_yy) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accyy += __shfl_down_sync(0xffffffffu, accyy, o);
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        // C fragment: row = lane/4, cols 2*(lane%4), +1
+        ws[t * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 0] = acc[t][0];
+        ws[t * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = acc[t][1];
+    }
+    if (lane == 0) ws[NT * 64] = accyy;
+    __syncthreads();
+    double* out = a.partial + (int64_t)blockIdx.x * a.partial_stride;
+    for (int e = threadIdx.x; e < NT * 64; e += kAsmThreads) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kAsmWarps; w++) t += sm[(size_t)w * a.warp_doubles + e];
+        out[(int64_t)tile_base * 64 + e] = t;
+    }
+    if (threadIdx.x == 0 && write_yy) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kAsmWarps; w++) t += sm[(size_t)w * a.warp_doubles + NT * 64];
+        out[a.partial_stride - 1] = t;
+    }
+}
+
+// =====================================================================================================
+// register-blocked variant
+// =====================================================================================================
+// shared table (uint16 function indices, premultiplied by kStride on load):
+//   rows1 [RT1][8][2] = (basis function, LL function)      cols1 [CT1][8] = RR function
+//   rows2 [RT2][8][2] = (phi*y function, L function)        cols2 [8]      = R function
+#ifndef BSDE_RB_MIN_BLOCKS
+#define BSDE_RB_MIN_BLOCKS 3
+#endif
+template <int RT1, int CT1, int RT2, int RB, int PB>
+__global__ void __launch_bounds__(kAsmThreads, BSDE_RB_MIN_BLOCKS)
+k_assemble_rb(AsmArgs a) {
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* ws = sm + (size_t)warp * a.warp_doubles;
+    unsigned short* stab = reinterpret_cast<unsigned short*>(sm + (size_t)kAsmWarps * a.warp_doubles);
+    for (int e = threadIdx.x; e < a.tab_entries; e += kAsmThreads) stab[e] = (unsigned short)(a.tab[e] * kStride);
+    __syncthreads();
+    const int g8 = lane >> 2;
+    // per-lane fragment sources (offsets in doubles): row tiles of M1 then of M2, two factors each; column tiles
+    constexpr int RT = RT1 + RT2;
+    int rlo[RT], rhi[RT];
+    int colA[CT1], colB;
+    {
+        const unsigned short* t = stab;
+#pragma unroll
+        for (int r = 0; r < RT1; r++) { rlo[r] = t[(r * 8 + g8) * 2]; rhi[r] = t[(r * 8 + g8) * 2 + 1]; }
+        t += RT1 * 16;
+#pragma unroll
+        for (int c = 0; c < CT1; c++) colA[c] = t[c * 8 + g8];
+        t += CT1 * 8;
+#pragma unroll
+        for (int r = 0; r < RT2; r++) { rlo[RT1 + r] = t[(r * 8 + g8) * 2]; rhi[RT1 + r] = t[(r * 8 + g8) * 2 + 1]; }
+        t += RT2 * 16;
+        colB = t[g8];
+    }
+
+    constexpr int NT = RT1 * CT1 + RT2;
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; t++) acc[t][0] = acc[t][1] = 0.0;
+    double accyy = 0.0;
+
+    const int64_t nchunks = (a.in.N + 31) / 32;
+    const int64_t warps_total = (int64_t)gridDim.x * kAsmWarps;
+    RawSample<RB, PB> raw;
+    load_raw<RB, PB>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
+    for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
+        accyy += stage_functions<RB, PB>(a, ws, lane, raw);
+        load_raw<RB, PB>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
+        __syncwarp();
+        const double* w = ws + (lane & 3);
+        // software pipeline inside one warp: the A fragment (a product of two staged factors) of row tile r+1 is
+        // formed, and the factors of row tile r+3 are requested, before the DMMAs of row tile r issue — the LDS and
+        // DMUL latencies are then covered by DMMA slots of the same warp
+        constexpr int R1 = (RT > 1) ? 1 : 0, R2 = (RT > 2) ? 2 : (2 % RT);
+        double av = w[rlo[0]] * w[rhi[0]];
+        double n0a = w[rlo[R1] + (RT > 1 ? 0 : 4)], n0b = w[rhi[R1] + (RT > 1 ? 0 : 4)];
+        double n1a = w[rlo[R2] + (RT > 2 ? 0 : 4)], n1b = w[rhi[R2] + (RT > 2 ? 0 : 4)];
+#pragma unroll 1
+        for (int step = 0; step < 8; step++, w += 4) {
+            double bc[CT1];
+#pragma unroll
+            for (int c = 0; c < CT1; c++) bc[c] = w[colA[c]];
+            const double b2 = w[colB];
+#pragma unroll
+            for (int r = 0; r < RT; r++) {
+                const double cur = av;
+                av = n0a * n0b;                       // row tile r+1
+                n0a = n1a; n0b = n1b;                 // row tile r+2
+                // row tile r+3: of this step, or of the next one (the 4 pad samples after the 32 staged ones make
+                // the look-ahead of the last step a harmless read)
+                const int nr = (r + 3) % RT;
+                const int no = ((r + 3) / RT) * 4;
+                n1a = w[rlo[nr] + no];
+                n1b = w[rhi[nr] + no];
+                if (r < RT1) {
+#pragma unroll
+                    for (int c = 0; c < CT1; c++) dmma884(acc[r * CT1 + c][0], acc[r * CT1 + c][1], cur, bc[c]);
+                } else {
+                    dmma884(acc[RT1 * CT1 + (r - RT1)][0], acc[RT1 * CT1 + (r - RT1)][1], cur, b2);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    write_partials<NT>(a, sm, ws, acc, accyy, lane, 0, true);
+}
+
+// =====================================================================================================
+// generic table-driven variant
+// =====================================================================================================
+struct TileOff { int r, c1, c2; };
+__device__ __forceinline__ TileOff unpack_tile(unsigned long long t) {
+    return {(int)(t & 0xffffu), (int)((t >> 16) & 0xffffu), (int)((t >> 32) & 0xffffu)};
+}
+
+// Four 8x8 output tiles over the 32 staged samples: per 4-sample step one DMMA.8x8x4 on each of four independent
+// accumulators, the B fragment formed as a product of two staged factors.
+__device__ __forceinline__ void tile_quad(const double* __restrict__ w, const unsigned long long* __restrict__ tab,
+                                          double (&c0)[2], double (&c1)[2], double (&c2)[2], double (&c3)[2]) {
+    const TileOff t0 = unpack_tile(tab[0]), t1 = unpack_tile(tab[8]), t2 = unpack_tile(tab[16]), t3 = unpack_tile(tab[24]);
+#pragma unroll 1
+    for (int step = 0; step < 8; step++) {     // not unrolled: ptxas otherwise regroups the DMMAs by accumulator
+        const int o = step * 4;
+        const double x0 = w[t0.r + o], p0 = w[t0.c1 + o] * w[t0.c2 + o];
+        const double x1 = w[t1.r + o], p1 = w[t1.c1 + o] * w[t1.c2 + o];
+        const double x2 = w[t2.r + o], p2 = w[t2.c1 + o] * w[t2.c2 + o];
+        const double x3 = w[t3.r + o], p3 = w[t3.c1 + o] * w[t3.c2 + o];
+        dmma884(c0[0], c0[1], x0, p0);
+        dmma884(c1[0], c1[1], x1, p1);
+        dmma884(c2[0], c2[1], x2, p2);
+        dmma884(c3[0], c3[1], x3, p3);
     }
 }
 
@@ -81,7 +309,6 @@ k_assemble(AsmArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* ws = sm + (size_t)warp * a.warp_doubles;
     const int group = blockIdx.y;
-    const int64_t N = a.in.N;
 
     // this group's tile table: per (tile, lane group) the staged-function offsets (doubles) of the A fragment row
     // and of the two B fragment factors, packed 3 x 16 bit
@@ -99,120 +326,45 @@ k_assemble(AsmArgs a) {
     for (int jb = 0; jb < NJ; jb++) acc[jb][0] = acc[jb][1] = 0.0;
     double accyy = 0.0;
 
-    const int64_t nchunks = (N + 31) / 32;
+    const int64_t nchunks = (a.in.N + 31) / 32;
     const int64_t warps_total = (int64_t)gridDim.x * kAsmWarps;
+    RawSample<RB, PB> raw;
+    load_raw<RB, PB>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
     for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
-        // ---------------- phase 1: lane = sample ----------------
-        const int64_t s = chunk * 32 + lane;
-        const bool valid = s < N;
-        const int64_t sc = valid ? s : N - 1;
-        const double vm = valid ? 1.0 : 0.0;
-        double Lv[RB], Rv[RB];
-#pragma unroll
-        for (int q = 0; q < RB; q++) {
-            Lv[q] = (q < a.rl) ? (a.L ? a.L[(int64_t)q * N + sc] : 1.0) : 0.0;
-            Rv[q] = (q < a.rr) ? (a.R ? a.R[(int64_t)q * N + sc] : 1.0) : 0.0;
-        }
-        const double yv = a.y[sc] * vm;
-        accyy = fma(yv, yv, accyy);
-        ws[lane] = 0.0;   // function 0 = ZERO
-        {
-            int idx = a.fLL;
-#pragma unroll
-            for (int q = 0; q < RB; q++)
-#pragma unroll
-                for (int q2 = q; q2 < RB; q2++)
-                    if (q < a.rl && q2 < a.rl) { ws[idx * kStride + lane] = Lv[q] * Lv[q2]; idx++; }
-            idx = a.fRR;
-#pragma unroll
-            for (int q = 0; q < RB; q++)
-#pragma unroll
-                for (int q2 = q; q2 < RB; q2++)
-                    if (q < a.rr && q2 < a.rr) { ws[idx * kStride + lane] = Rv[q] * Rv[q2]; idx++; }
-#pragma unroll
-            for (int q = 0; q < RB; q++) {
-                if (q < a.rl) ws[(a.fL + q) * kStride + lane] = Lv[q];
-                if (q < a.rr) ws[(a.fR + q) * kStride + lane] = Rv[q];
-            }
-        }
-        if (a.mono) {
-            const double x = a.in.data[(int64_t)a.j * N + sc];
-            double pw = vm;
-#pragma unroll
-            for (int k = 0; k < 2 * PB - 1; k++) {
-                if (k < a.nB) ws[(a.fRow1 + k) * kStride + lane] = pw;
-                if (k < a.in.p) ws[(a.fRow2 + k) * kStride + lane] = pw * yv;
-                pw *= x;
-            }
-        } else {
-            double phi[PB];
-            basis_values<PB>(a.in, a.j, sc, 0, phi);
-            int idx = a.fRow1;
-#pragma unroll
-            for (int m = 0; m < PB; m++)
-#pragma unroll
-                for (int m2 = m; m2 < PB; m2++)
-                    if (m < a.in.p && m2 < a.in.p) { ws[idx * kStride + lane] = vm * phi[m] * phi[m2]; idx++; }
-#pragma unroll
-            for (int m = 0; m < PB; m++)
-                if (m < a.in.p) ws[(a.fRow2 + m) * kStride + lane] = phi[m] * yv;
-        }
+        accyy += stage_functions<RB, PB>(a, ws, lane, raw);
+        load_raw<RB, PB>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
         __syncwarp();
-        // ---------------- phase 2: DMMA over the staged 32 samples, two independent tiles at a time ----------------
         const double* w = ws + (lane & 3);
 #pragma unroll
-        for (int jb = 0; jb < NJ; jb += 2) tile_pair(w, mytab[jb * 8], mytab[(jb + 1) * 8], acc[jb], acc[jb + 1]);
+        for (int jb = 0; jb < NJ; jb += 4) tile_quad(w, mytab + jb * 8, acc[jb], acc[jb + 1], acc[jb + 2], acc[jb + 3]);
         __syncwarp();
     }
-
-    // ---------------- epilogue: fixed-order sum over the CTA's warps ----------------
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) accyy += __shfl_down_sync(0xffffffffu, accyy, o);
-    __syncthreads();
-#pragma unroll
-    for (int jb = 0; jb < NJ; jb++) {
-        // C fragment: row = lane/4, cols 2*(lane%4), +1
-        ws[jb * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 0] = acc[jb][0];
-        ws[jb * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = acc[jb][1];
-    }
-    if (lane == 0) ws[NJ * 64] = accyy;
-    __syncthreads();
-    double* out = a.partial + (int64_t)blockIdx.x * a.partial_stride;
-    for (int e = threadIdx.x; e < NJ * 64; e += kAsmThreads) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < kAsmWarps; w++) t += sm[(size_t)w * a.warp_doubles + e];
-        out[(int64_t)group * NJ * 64 + e] = t;
-    }
-    if (threadIdx.x == 0 && group == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < kAsmWarps; w++) t += sm[(size_t)w * a.warp_doubles + NJ * 64];
-        out[a.partial_stride - 1] = t;
-    }
+    write_partials<NJ>(a, sm, ws, acc, accyy, lane, group * NJ, group == 0);
 }
 
-// moments[e] = sum over partial rows of partial[row][gather[e]].  One block = 32 consecutive moments x 8 row
-// lanes: warp w adds rows w, w+8, ... in order, then the 8 warp sums are added in warp order, so the result is
+// moments[e] = sum over partial rows of partial[row][gather[e]].  One block = 32 consecutive moments x 32 row
+// lanes: warp w adds rows w, w+32, ... in order, then the warp sums are added in warp order, so the result is
 // a fixed summation tree of the launch shape (bitwise reproducible).
-constexpr int kRedWarps = 8;
+constexpr int kRedWarps = 32;
 __global__ void __launch_bounds__(32 * kRedWarps)
 k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride,
                 const int32_t* __restrict__ gather, int n_mom, double* __restrict__ moments) {
     __shared__ double part[kRedWarps][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
-    double a0 = 0.0, a1 = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (e < n_mom) {
         const int32_t g = gather[e];
         int q = w;
-        for (; q + kRedWarps < rows; q += 2 * kRedWarps) {
+        for (; q + 3 * kRedWarps < rows; q += 4 * kRedWarps) {
             a0 += partial[(int64_t)q * stride + g];
             a1 += partial[(int64_t)(q + kRedWarps) * stride + g];
+            a2 += partial[(int64_t)(q + 2 * kRedWarps) * stride + g];
+            a3 += partial[(int64_t)(q + 3 * kRedWarps) * stride + g];
         }
-        if (q < rows) a0 += partial[(int64_t)q * stride + g];
+        for (; q < rows; q += kRedWarps) a0 += partial[(int64_t)q * stride + g];
     }
-    part[w][lane] = a0 + a1;
+    part[w][lane] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     if (w == 0 && e < n_mom) {
         double t = 0.0;
@@ -222,51 +374,51 @@ k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride,
     }
 }
 
-template <int NJ, int RB, int PB>
-int launch_t(const AsmPlan& plan, const AsmArgs& args, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        BSDE_CUDA_OK(cudaFuncSetAttribute(k_assemble<NJ, RB, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+// ---- dispatch ----------------------------------------------------------------------------------------
+enum { OP_LAUNCH = 0, OP_OCCUPANCY = 1 };
+
+template <class K>
+int run_kernel(K kernel, int op, const AsmPlan& plan, const AsmArgs* args, cudaStream_t st, int* occ) {
+    if (op == OP_OCCUPANCY) {
+        BSDE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kernel, kAsmThreads, plan.smem_bytes));
+        return 0;
     }
     dim3 grid(plan.grid_x, plan.n_groups);
-    k_assemble<NJ, RB, PB><<<grid, kAsmThreads, plan.smem_bytes, st>>>(args);
+    kernel<<<grid, kAsmThreads, plan.smem_bytes, st>>>(*args);
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <int NJ>
-int launch_nj(const AsmPlan& plan, const AsmArgs& args, cudaStream_t st) {
-    const int rb = std::max(plan.rl, plan.rr);
-    const bool p4 = plan.p <= 4;
-    if (rb <= 4) return p4 ? launch_t<NJ, 4, 4>(plan, args, st) : launch_t<NJ, 4, 8>(plan, args, st);
-    return p4 ? launch_t<NJ, 8, 4>(plan, args, st) : launch_t<NJ, 8, 8>(plan, args, st);
+template <int RB, int PB>
+int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* occ) {
+    if (P.rb_class >= 0) {
+        switch (P.rb_class) {
+            case 0: return run_kernel(k_assemble_rb<1, 1, 1, RB, PB>, op, P, a, st, occ);
+            case 1: return run_kernel(k_assemble_rb<2, 1, 1, RB, PB>, op, P, a, st, occ);
+            case 2: return run_kernel(k_assemble_rb<4, 1, 2, RB, PB>, op, P, a, st, occ);
+            case 3: return run_kernel(k_assemble_rb<2, 2, 1, RB, PB>, op, P, a, st, occ);
+            default: return run_kernel(k_assemble_rb<9, 2, 2, RB, PB>, op, P, a, st, occ);
+        }
+    }
+    if (P.NJ == 4) return run_kernel(k_assemble<4, RB, PB>, op, P, a, st, occ);
+    if (P.NJ == 8) return run_kernel(k_assemble<8, RB, PB>, op, P, a, st, occ);
+    return run_kernel(k_assemble<16, RB, PB>, op, P, a, st, occ);
 }
 
+int dispatch(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* occ) {
+    const int rb = std::max(P.rl, P.rr);
+    const bool p4 = P.p <= 4;
+    if (rb <= 4) return p4 ? dispatch_rbpb<4, 4>(op, P, a, st, occ) : dispatch_rbpb<4, 8>(op, P, a, st, occ);
+    return p4 ? dispatch_rbpb<8, 4>(op, P, a, st, occ) : dispatch_rbpb<8, 8>(op, P, a, st, occ);
+}
 
-template <int NJ, int RB, int PB>
-int occ_t(size_t smem, int* out) {
-    BSDE_CUDA_OK(cudaFuncSetAttribute(k_assemble<NJ, RB, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k_assemble<NJ, RB, PB>, kAsmThreads, smem));
-    return 0;
-}
-template <int NJ>
-int occ_nj(const AsmPlan& plan, int* out) {
-    const int rb = std::max(plan.rl, plan.rr);
-    const bool p4 = plan.p <= 4;
-    if (rb <= 4) return p4 ? occ_t<NJ, 4, 4>(plan.smem_bytes, out) : occ_t<NJ, 4, 8>(plan.smem_bytes, out);
-    return p4 ? occ_t<NJ, 8, 4>(plan.smem_bytes, out) : occ_t<NJ, 8, 8>(plan.smem_bytes, out);
-}
-// resident CTAs per SM of the kernel instance this plan launches (registers and shared memory)
-int asm_blocks_per_sm(const AsmPlan& plan, int* out) {
-    if (plan.NJ == 4) return occ_nj<4>(plan, out);
-    if (plan.NJ == 8) return occ_nj<8>(plan, out);
-    return occ_nj<16>(plan, out);
-}
+// tile-count classes of the register-blocked kernel: (row tiles of M1, column tiles of M1, row tiles of M2)
+const int kRbClasses[5][3] = {{1, 1, 1}, {2, 1, 1}, {4, 1, 2}, {2, 2, 1}, {9, 2, 2}};
 
 }  // namespace
 
-int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int sm_count) {
+int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int sm_count, int force_generic) {
     if (rl < 1 || rr < 1 || p < 1 || rl > 8 || rr > 8 || p > kMaxP)
         return fail_msg(2, "assembly: core shape (%d,%d,%d) outside the supported range (ranks <= 8, p <= %d)", rl, p, rr, kMaxP);
     P.rl = rl; P.p = p; P.rr = rr; P.mono = mono;
@@ -281,99 +433,132 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
     P.fR = P.fL + rl;
     P.fRow2 = P.fR + rr;
     P.F = P.fRow2 + p;
-
-    struct Col { int f1, f2, key1, key2; };
-    // GEMM 1 columns: (lambda, rho) in two parts so that most fragment factors stay in registers
-    std::vector<Col> cols1;
-    const int full = P.nRR / 8;
-    for (int q = 0; q < full; q++)
-        for (int lam = 0; lam < P.nLL; lam++)
-            for (int i = 0; i < 8; i++) cols1.push_back({P.fLL + lam, P.fRR + 8 * q + i, lam, 8 * q + i});
-    for (int rho = full * 8; rho < P.nRR; rho++)
-        for (int lam = 0; lam < P.nLL; lam++) cols1.push_back({P.fLL + lam, P.fRR + rho, lam, rho});
-    while (cols1.size() % 8) cols1.push_back({0, 0, -1, -1});
-    std::vector<Col> cols2;
-    for (int a = 0; a < rl; a++)
-        for (int b = 0; b < rr; b++) cols2.push_back({P.fL + a, P.fR + b, a, b});
-    while (cols2.size() % 8) cols2.push_back({0, 0, -1, -1});
-    const int RT1 = (P.nB + 7) / 8, CT1 = (int)cols1.size() / 8;
-    const int RT2 = (p + 7) / 8, CT2 = (int)cols2.size() / 8;
-    P.n_jobs = RT1 * CT1 + RT2 * CT2;
-    P.NJ = P.n_jobs <= 4 ? 4 : (P.n_jobs <= 8 ? 8 : 16);
-    P.n_groups = (P.n_jobs + P.NJ - 1) / P.NJ;
-    const int total = P.n_groups * P.NJ;
-    P.partial_stride = (int64_t)total * 64 + 1;
     P.n_mom = P.nB * P.nLL * P.nRR + p * rl * rr + 1;
-
-    std::vector<uint16_t> tab((size_t)total * 8 * 3, 0);
-    std::vector<uint8_t> flags(total, 7);
     P.h_gather.assign(P.n_mom, 0);
-    int job = 0;
-    for (int ct = 0; ct < CT1; ct++)
-        for (int rt = 0; rt < RT1; rt++, job++)
-            for (int i = 0; i < 8; i++) {
-                const int beta = rt * 8 + i;
-                tab[((size_t)job * 8 + i) * 3 + 0] = (uint16_t)(beta < P.nB ? P.fRow1 + beta : 0);
-                const Col& c = cols1[ct * 8 + i];
-                tab[((size_t)job * 8 + i) * 3 + 1] = (uint16_t)c.f1;
-                tab[((size_t)job * 8 + i) * 3 + 2] = (uint16_t)c.f2;
-                if (c.key1 >= 0)
-                    for (int r8 = 0; r8 < 8; r8++) {
-                        const int b2 = rt * 8 + r8;
-                        if (b2 < P.nB) P.h_gather[((size_t)b2 * P.nLL + c.key1) * P.nRR + c.key2] = job * 64 + r8 * 8 + i;
-                    }
-            }
     const int base2 = P.nB * P.nLL * P.nRR;
-    for (int ct = 0; ct < CT2; ct++)
-        for (int rt = 0; rt < RT2; rt++, job++)
-            for (int i = 0; i < 8; i++) {
-                const int m = rt * 8 + i;
-                tab[((size_t)job * 8 + i) * 3 + 0] = (uint16_t)(m < p ? P.fRow2 + m : 0);
-                const Col& c = cols2[ct * 8 + i];
-                tab[((size_t)job * 8 + i) * 3 + 1] = (uint16_t)c.f1;
-                tab[((size_t)job * 8 + i) * 3 + 2] = (uint16_t)c.f2;
-                if (c.key1 >= 0)
-                    for (int r8 = 0; r8 < 8; r8++) {
-                        const int m2 = rt * 8 + r8;
-                        if (m2 < p) P.h_gather[base2 + ((size_t)m2 * rl + c.key1) * rr + c.key2] = job * 64 + r8 * 8 + i;
-                    }
-            }
-    P.h_gather[P.n_mom - 1] = (int32_t)(P.partial_stride - 1);
-    // reload flags: a fragment source is re-read only when some lane group's function differs from the previous tile
-    for (int jb = 0; jb < total; jb++) {
-        if (jb % P.NJ == 0) { flags[jb] = 7; continue; }
-        uint8_t f = 0;
-        for (int i = 0; i < 8; i++)
-            for (int k = 0; k < 3; k++)
-                if (tab[((size_t)jb * 8 + i) * 3 + k] != tab[((size_t)(jb - 1) * 8 + i) * 3 + k]) f |= (uint8_t)(1 << k);
-        flags[jb] = f;
-    }
+    std::vector<uint16_t> tab;
+    size_t tab_smem = 0;
+    int n_tiles = 0;
 
-    const int warp_doubles = std::max(P.F * kStride, P.NJ * 64 + 1);
-    P.smem_bytes = (size_t)kAsmWarps * warp_doubles * sizeof(double) + (size_t)P.NJ * 8 * sizeof(unsigned long long);
+    // ---- register-blocked layout: rows (beta, lambda), columns rho; M2 rows (m, a), columns b ----
+    const int rows1 = P.nB * P.nLL, rows2 = p * rl;
+    const int needRT1 = (rows1 + 7) / 8, needCT1 = (P.nRR + 7) / 8, needRT2 = (rows2 + 7) / 8;
+    P.rb_class = -1;
+    if (!force_generic)
+        for (int k = 0; k < 5; k++)
+            if (needRT1 <= kRbClasses[k][0] && needCT1 <= kRbClasses[k][1] && needRT2 <= kRbClasses[k][2]) { P.rb_class = k; break; }
+
+    if (P.rb_class >= 0) {
+        const int RT1 = kRbClasses[P.rb_class][0], CT1 = kRbClasses[P.rb_class][1], RT2 = kRbClasses[P.rb_class][2];
+        n_tiles = RT1 * CT1 + RT2;
+        P.NJ = n_tiles; P.n_groups = 1; P.n_jobs = n_tiles;
+        tab.assign((size_t)RT1 * 16 + CT1 * 8 + RT2 * 16 + 8, 0);
+        uint16_t* t = tab.data();
+        for (int r = 0; r < RT1 * 8; r++)
+            if (r < rows1) { t[r * 2] = (uint16_t)(P.fRow1 + r / P.nLL); t[r * 2 + 1] = (uint16_t)(P.fLL + r % P.nLL); }
+        t += RT1 * 16;
+        for (int c = 0; c < CT1 * 8; c++) t[c] = (uint16_t)(c < P.nRR ? P.fRR + c : 0);
+        t += CT1 * 8;
+        for (int r = 0; r < RT2 * 8; r++)
+            if (r < rows2) { t[r * 2] = (uint16_t)(P.fRow2 + r / rl); t[r * 2 + 1] = (uint16_t)(P.fL + r % rl); }
+        t += RT2 * 16;
+        for (int c = 0; c < 8; c++) t[c] = (uint16_t)(c < rr ? P.fR + c : 0);
+        P.tab_entries = (int)tab.size();
+        tab_smem = tab.size() * sizeof(uint16_t);
+        for (int beta = 0; beta < P.nB; beta++)
+            for (int lam = 0; lam < P.nLL; lam++)
+                for (int rho = 0; rho < P.nRR; rho++) {
+                    const int row = beta * P.nLL + lam;
+                    const int tile = (row / 8) * CT1 + rho / 8;
+                    P.h_gather[((size_t)beta * P.nLL + lam) * P.nRR + rho] = tile * 64 + (row % 8) * 8 + rho % 8;
+                }
+        for (int m = 0; m < p; m++)
+            for (int a = 0; a < rl; a++)
+                for (int b = 0; b < rr; b++) {
+                    const int row = m * rl + a;
+                    const int tile = RT1 * CT1 + row / 8;
+                    P.h_gather[base2 + ((size_t)m * rl + a) * rr + b] = tile * 64 + (row % 8) * 8 + b;
+                }
+    } else {
+        // ---- generic layout: rows beta, columns (lambda, rho) pairs; M2 rows m, columns (a, b) ----
+        struct Col { int f1, f2, key1, key2; };
+        std::vector<Col> cols1;
+        const int full = P.nRR / 8;
+        for (int q = 0; q < full; q++)
+            for (int lam = 0; lam < P.nLL; lam++)
+                for (int i = 0; i < 8; i++) cols1.push_back({P.fLL + lam, P.fRR + 8 * q + i, lam, 8 * q + i});
+        for (int rho = full * 8; rho < P.nRR; rho++)
+            for (int lam = 0; lam < P.nLL; lam++) cols1.push_back({P.fLL + lam, P.fRR + rho, lam, rho});
+        while (cols1.size() % 8) cols1.push_back({0, 0, -1, -1});
+        std::vector<Col> cols2;
+        for (int a = 0; a < rl; a++)
+            for (int b = 0; b < rr; b++) cols2.push_back({P.fL + a, P.fR + b, a, b});
+        while (cols2.size() % 8) cols2.push_back({0, 0, -1, -1});
+        const int RT1 = (P.nB + 7) / 8, CT1 = (int)cols1.size() / 8;
+        const int RT2 = (p + 7) / 8, CT2 = (int)cols2.size() / 8;
+        P.n_jobs = RT1 * CT1 + RT2 * CT2;
+        P.NJ = P.n_jobs <= 4 ? 4 : (P.n_jobs <= 8 ? 8 : 16);
+        P.n_groups = (P.n_jobs + P.NJ - 1) / P.NJ;
+        n_tiles = P.n_groups * P.NJ;
+        tab.assign((size_t)n_tiles * 8 * 3, 0);
+        int job = 0;
+        for (int ct = 0; ct < CT1; ct++)
+            for (int rt = 0; rt < RT1; rt++, job++)
+                for (int i = 0; i < 8; i++) {
+                    const int beta = rt * 8 + i;
+                    tab[((size_t)job * 8 + i) * 3 + 0] = (uint16_t)(beta < P.nB ? P.fRow1 + beta : 0);
+                    const Col& c = cols1[ct * 8 + i];
+                    tab[((size_t)job * 8 + i) * 3 + 1] = (uint16_t)c.f1;
+                    tab[((size_t)job * 8 + i) * 3 + 2] = (uint16_t)c.f2;
+                    if (c.key1 >= 0)
+                        for (int r8 = 0; r8 < 8; r8++) {
+                            const int b2 = rt * 8 + r8;
+                            if (b2 < P.nB) P.h_gather[((size_t)b2 * P.nLL + c.key1) * P.nRR + c.key2] = job * 64 + r8 * 8 + i;
+                        }
+                }
+        for (int ct = 0; ct < CT2; ct++)
+            for (int rt = 0; rt < RT2; rt++, job++)
+                for (int i = 0; i < 8; i++) {
+                    const int m = rt * 8 + i;
+                    tab[((size_t)job * 8 + i) * 3 + 0] = (uint16_t)(m < p ? P.fRow2 + m : 0);
+                    const Col& c = cols2[ct * 8 + i];
+                    tab[((size_t)job * 8 + i) * 3 + 1] = (uint16_t)c.f1;
+                    tab[((size_t)job * 8 + i) * 3 + 2] = (uint16_t)c.f2;
+                    if (c.key1 >= 0)
+                        for (int r8 = 0; r8 < 8; r8++) {
+                            const int m2 = rt * 8 + r8;
+                            if (m2 < p) P.h_gather[base2 + ((size_t)m2 * rl + c.key1) * rr + c.key2] = job * 64 + r8 * 8 + i;
+                        }
+                }
+        P.tab_entries = 0;
+        tab_smem = (size_t)P.NJ * 8 * sizeof(unsigned long long);
+    }
+    P.partial_stride = (int64_t)n_tiles * 64 + 1;
+    P.h_gather[P.n_mom - 1] = (int32_t)(P.partial_stride - 1);
+
+    const int tiles_per_cta = P.rb_class >= 0 ? n_tiles : P.NJ;
+    P.warp_doubles = std::max(P.F * kStride + 16, tiles_per_cta * 64 + 1);    // +16: look-ahead reads of the pipelined loop
+    P.smem_bytes = (size_t)kAsmWarps * P.warp_doubles * sizeof(double) + ((tab_smem + 15) & ~(size_t)15);
     if (P.smem_bytes > 200 * 1024) return fail_msg(2, "assembly: core shape (%d,%d,%d) needs %zu B of shared memory", rl, p, rr, P.smem_bytes);
     const int64_t nchunks = (N + 31) / 32;
     const int64_t want = (nchunks + kAsmWarps - 1) / kAsmWarps;
     int per_sm = 1;
-    { const int rc = asm_blocks_per_sm(P, &per_sm); if (rc) return rc; }
+    { const int rc = dispatch(OP_OCCUPANCY, P, nullptr, nullptr, &per_sm); if (rc) return rc; }
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 6) per_sm = 6;
     P.grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count * per_sm));
 
     BSDE_CUDA_OK(cudaMalloc(&P.d_tab, tab.size() * sizeof(uint16_t)));
-    BSDE_CUDA_OK(cudaMalloc(&P.d_flags, flags.size()));
     BSDE_CUDA_OK(cudaMalloc(&P.d_gather, P.h_gather.size() * sizeof(int32_t)));
     BSDE_CUDA_OK(cudaMemcpy(P.d_tab, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    BSDE_CUDA_OK(cudaMemcpy(P.d_flags, flags.data(), flags.size(), cudaMemcpyHostToDevice));
     BSDE_CUDA_OK(cudaMemcpy(P.d_gather, P.h_gather.data(), P.h_gather.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     return 0;
 }
 
 void asm_plan_free(AsmPlan& P) {
     if (P.d_tab) cudaFree(P.d_tab);
-    if (P.d_flags) cudaFree(P.d_flags);
     if (P.d_gather) cudaFree(P.d_gather);
-    P.d_tab = nullptr; P.d_flags = nullptr; P.d_gather = nullptr;
+    P.d_tab = nullptr; P.d_gather = nullptr;
 }
 
 int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, const double* R, const double* y,
@@ -382,13 +567,10 @@ int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, 
     a.in = in; a.j = j; a.L = L; a.R = R; a.y = y;
     a.rl = P.rl; a.rr = P.rr; a.mono = P.mono; a.nB = P.nB;
     a.F = P.F; a.fLL = P.fLL; a.fRR = P.fRR; a.fRow1 = P.fRow1; a.fL = P.fL; a.fR = P.fR; a.fRow2 = P.fRow2;
-    a.warp_doubles = (int)((P.smem_bytes - (size_t)P.NJ * 8 * sizeof(unsigned long long)) / sizeof(double) / kAsmWarps);
-    a.tab = P.d_tab; a.flags = P.d_flags;
+    a.warp_doubles = P.warp_doubles;
+    a.tab = P.d_tab; a.tab_entries = P.tab_entries;
     a.partial = partial; a.partial_stride = P.partial_stride;
-    int rc;
-    if (P.NJ == 4) rc = launch_nj<4>(P, a, st);
-    else if (P.NJ == 8) rc = launch_nj<8>(P, a, st);
-    else rc = launch_nj<16>(P, a, st);
+    const int rc = dispatch(OP_LAUNCH, P, &a, st, nullptr);
     if (rc) return rc;
     if (mid) BSDE_CUDA_OK(cudaEventRecord(mid, st));
     k_moment_reduce<<<(P.n_mom + 31) / 32, 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride, P.d_gather, P.n_mom, moments);

@@ -56,17 +56,9 @@ __device__ __forceinline__ void monomials_cr(double x, double (&out)[PB]) {
     }
 }
 
-// Basis values (deriv = 0), first (1) or second (2) derivatives for asset j, sample s.
-// Entries m >= in.p are set to zero.
+// Fused bases: values (deriv = 0), first (1) or second (2) derivatives at the point x.  Entries m >= in.p are zero.
 template <int PB>
-__device__ __forceinline__ void basis_values(const Inputs& in, int j, int64_t s, int deriv, double (&phi)[PB]) {
-    if (in.kind == BASIS_PHI) {
-        const double* src = (deriv == 0 ? in.data : in.ddata) + ((int64_t)j * in.p) * in.N + s;
-#pragma unroll
-        for (int m = 0; m < PB; m++) phi[m] = (m < in.p) ? __ldg(src + (int64_t)m * in.N) : 0.0;
-        return;
-    }
-    const double x = __ldg(in.data + (int64_t)j * in.N + s);
+__device__ __forceinline__ void basis_from_x(const Inputs& in, double x, int deriv, double (&phi)[PB]) {
     if (in.kind == BASIS_POLY) {
         double mono[PB];
         monomials_cr<PB>(x, mono);
@@ -95,6 +87,19 @@ __device__ __forceinline__ void basis_values(const Inputs& in, int j, int64_t s,
         }
         phi[m] = yv;
     }
+}
+
+// Basis values (deriv = 0), first (1) or second (2) derivatives for asset j, sample s.
+// Entries m >= in.p are set to zero.
+template <int PB>
+__device__ __forceinline__ void basis_values(const Inputs& in, int j, int64_t s, int deriv, double (&phi)[PB]) {
+    if (in.kind == BASIS_PHI) {
+        const double* src = (deriv == 0 ? in.data : in.ddata) + ((int64_t)j * in.p) * in.N + s;
+#pragma unroll
+        for (int m = 0; m < PB; m++) phi[m] = (m < in.p) ? __ldg(src + (int64_t)m * in.N) : 0.0;
+        return;
+    }
+    basis_from_x<PB>(in, __ldg(in.data + (int64_t)j * in.N + s), deriv, phi);
 }
 
 #define BSDE_CUDA_OK(expr)                                                                   \

@@ -26,19 +26,21 @@ struct AsmPlan {
     int nLL = 0, nRR = 0, nB = 0;
     int F = 0;                                    // staged per-sample functions
     int fLL = 0, fRR = 0, fRow1 = 0, fL = 0, fR = 0, fRow2 = 0;   // first index of each family (0 = ZERO)
-    int n_jobs = 0, NJ = 0, n_groups = 0;         // 8x8 output tiles; tiles per warp; blockIdx.y groups
+    int rb_class = -1;                            // >= 0: register-blocked kernel of that tile-count class; -1: generic
+    int n_jobs = 0, NJ = 0, n_groups = 0;         // 8x8 output tiles; tiles per CTA; blockIdx.y groups
     int n_mom = 0;                                // canonical moments: nB*nLL*nRR + p*rl*rr + 1
     int n = 0;                                    // unknowns r_l*p*r_r
     int grid_x = 0;                               // CTAs along the sample axis (= number of partial rows)
-    int64_t partial_stride = 0;                   // doubles per partial row = n_groups*NJ*64 + 1
+    int64_t partial_stride = 0;                   // doubles per partial row = tiles*64 + 1
+    int warp_doubles = 0;                         // shared-memory doubles per warp
+    int tab_entries = 0;
     size_t smem_bytes = 0;
-    uint16_t* d_tab = nullptr;                    // [n_groups*NJ][8][3]  (row fn, col fn 1, col fn 2) per lane group
-    uint8_t* d_flags = nullptr;                   // [n_groups*NJ] bit0 reload row, bit1 reload c1, bit2 reload c2
+    uint16_t* d_tab = nullptr;                    // fragment-source table (layout depends on the variant)
     int32_t* d_gather = nullptr;                  // [n_mom] canonical moment -> slot in a partial row
     std::vector<int32_t> h_gather;
 };
 
-int asm_plan_build(AsmPlan& plan, int rl, int p, int rr, int mono, int64_t N, int sm_count);
+int asm_plan_build(AsmPlan& plan, int rl, int p, int rr, int mono, int64_t N, int sm_count, int force_generic = 0);
 void asm_plan_free(AsmPlan& plan);
 // Launches the assembly kernel and the partial reduction; `moments` (n_mom doubles, device) receives
 // [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y].

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "libbsde_b200.so"))
+# BSDE_B200_LIB selects an alternative build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("BSDE_B200_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "libbsde_b200.so"))
 
 BASIS_PHI, BASIS_POLY, BASIS_LEGENDRE = 0, 1, 2
 SOLVER_IDS = {"lstsq": 0, "lu": 1, "qr": 2, "solve": 3}
