@@ -541,3 +541,50 @@ def implicit_scheme(X, xi, model, basis="polynomial", p=3, ranks=None, n_iter=20
             Y_nk = tt_eval(cores, phis)
         Y[:, n] = Y_nk
     return Y, cores
+
+
+# --------------------------------------------------------------------------------------
+# Philox4x32-10 counter-based increments — no reference counterpart: restates the stream of the CUDA path
+# kernel (bsde-tensor-networks_b200/csrc/model.cu: philox_normal_pair) so that tests can pin it bit for bit.
+# --------------------------------------------------------------------------------------
+
+
+def _philox4x32_10(c, k0, k1):
+    """c: (..., 4) uint32 counters, k0/k1 scalar keys -> (..., 4) uint32 (Salmon et al., SC'11)."""
+    c = np.array(c, dtype=np.uint64)
+    k0 = np.uint64(k0)
+    k1 = np.uint64(k1)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[..., 0]
+        p1 = M1 * c[..., 2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[..., 1] ^ k0, lo1, hi0 ^ c[..., 3] ^ k1, lo0], axis=-1)
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return c.astype(np.uint64)
+
+
+def philox_increments(seed, n_samples, d, steps, sample_offset=0):
+    """xi [steps+1][d][N] exactly as k_paths draws it.  One Philox block per (sample, asset, odd step n) with
+    counter = (sample lo, sample hi, asset, n >> 1) and key = (seed lo, seed hi) yields two uniforms of 53 bits;
+    Box-Muller's cosine branch is the increment of step n, its sine branch the increment of step n + 1.
+    xi[0] = 0 (never used, path.py:34)."""
+    xi = np.zeros((steps + 1, d, n_samples))
+    s = np.arange(n_samples, dtype=np.uint64) + np.uint64(sample_offset)
+    lo, hi = s & np.uint64(0xFFFFFFFF), s >> np.uint64(32)
+    for n in range(1, steps + 1, 2):
+        for j in range(d):
+            ctr = np.stack([lo, hi, np.full_like(s, j), np.full_like(s, n >> 1)], axis=-1)
+            r = _philox4x32_10(ctr, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+            a = (r[:, 1] << np.uint64(32)) | r[:, 0]
+            b = (r[:, 3] << np.uint64(32)) | r[:, 2]
+            u1 = ((a >> np.uint64(11)).astype(np.float64) + 1.0) * (1.0 / 9007199254740992.0)
+            u2 = (b >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+            rad = np.sqrt(-2.0 * np.log(u1))
+            xi[n, j] = rad * np.cos(2 * np.pi * u2)
+            if n + 1 <= steps:
+                xi[n + 1, j] = rad * np.sin(2 * np.pi * u2)
+    return xi

@@ -1,0 +1,129 @@
+"""CPU: host-side mirror of the reference interface — named-axis cores, the train container, the wire format of the
+C ABI, argument checking.  (Everything numerical lives behind the library and is tested under -m gpu.)"""
+import numpy as np
+import pytest
+
+import oracle.tt_oracle as O
+from bsde_solver import reload_backend
+from bsde_solver.core.tensor.tensor_core import TensorCore
+from bsde_solver.core.tensor.tensor_network import TensorNetwork
+from bsde_solver.core.tensor.tensor_train import TensorTrain, left_unfold, pack_cores, right_unfold, unpack_cores
+
+
+def test_reload_backend_contract():
+    reload_backend("numpy")
+    reload_backend("cupy")          # accepted name; there is one CUDA backend behind both
+    with pytest.raises(ValueError):
+        reload_backend("jax")
+
+
+def test_tensor_core_unfold_rename_like():
+    a = np.arange(24.0).reshape(2, 3, 4)
+    c = TensorCore(a, indices=("r_0", "m_1", "r_1"), name="core_0")
+    lu, ru = left_unfold(c), right_unfold(c)
+    assert lu.shape == (6, 4) and lu.indices == ("r_0+m_1", "r_1")
+    assert ru.shape == (2, 12) and ru.indices == ("r_0", "m_1+r_1")
+    np.testing.assert_array_equal(np.asarray(lu), a.reshape(6, 4))
+    t = c.unfold("r_1", ("m_1", "r_0"))
+    np.testing.assert_array_equal(np.asarray(t), a.transpose(2, 1, 0).reshape(4, 6))
+    rest = c.unfold("m_1", -1)
+    assert rest.shape == (3, 8) and rest.indices == ("m_1", "r_0+r_1")
+    r = c.copy().rename("r_*", "s_*")
+    assert r.indices == ("s_0", "m_1", "s_1") and c.indices == ("r_0", "m_1", "r_1")
+    k = TensorCore.like(np.arange(24.0), c)
+    assert k.shape == (2, 3, 4) and k.indices == c.indices and k.name == "core_0"
+    assert c.size_at("m_1") == 3
+    assert "r_0 {2}" in repr(c)
+
+
+def test_tensor_train_container_and_wire_format():
+    np.random.seed(3)
+    tt = TensorTrain([3, 3, 3, 3], [1, 2, 3, 2, 1])
+    assert tt.order == 4 and list(tt.cores) == ["core_0", "core_1", "core_2", "core_3"]
+    assert tt.cores["core_1"].indices == ("r_1", "m_2", "r_2") and tt.cores["core_1"].shape == (2, 3, 3)
+    np.random.seed(3)
+    ref = O.randomize_cores([3, 3, 3, 3], [1, 2, 3, 2, 1])
+    np.random.seed(3)
+    assert tt.randomize() is tt
+    for a, b in zip(tt.cores.values(), ref):          # same draws from the global numpy stream as the reference
+        np.testing.assert_array_equal(np.asarray(a), b)
+    ranks, flat = pack_cores(tt)
+    assert ranks.tolist() == [1, 2, 3, 2, 1] and flat.size == 6 + 18 + 18 + 6
+    np.testing.assert_array_equal(flat[6:24], ref[1].ravel())
+    tt2 = TensorTrain([3, 3, 3, 3], [1, 2, 3, 2, 1])
+    unpack_cores(tt2, ranks, flat)
+    for a, b in zip(tt2.cores.values(), ref):
+        np.testing.assert_array_equal(np.asarray(a), b)
+    assert tt2.cores["core_2"].indices == ("r_2", "m_3", "r_3") and tt2.cores["core_2"].name == "core_2"
+    # rank growth (SALSA): unpack with new ranks keeps names and labels
+    grown = np.zeros(1 * 3 * 3 + 3 * 3 * 3 + 3 * 3 * 2 + 2 * 3 * 1)
+    unpack_cores(tt2, [1, 3, 3, 2, 1], grown)
+    assert tt2.cores["core_0"].shape == (1, 3, 3) and tt2.cores["core_1"].shape == (3, 3, 3)
+    cp = tt.copy()
+    cp.cores["core_0"][:] = 0
+    assert np.asarray(tt.cores["core_0"]).any()
+
+
+def test_from_tensor_reconstructs():
+    rng = np.random.RandomState(0)
+    full = np.einsum("ia,ajb,bk->ijk", rng.randn(3, 2), rng.randn(2, 4, 2), rng.randn(2, 3))
+    tt = TensorTrain.from_tensor(full, [1, 2, 2, 1])
+    cores = [np.asarray(c) for c in tt.cores.values()]
+    back = np.einsum("xia,ajb,bky->ijk", *cores)
+    np.testing.assert_allclose(back, full, atol=1e-12)
+
+
+def test_tensor_network_contract_and_sample():
+    rng = np.random.RandomState(1)
+    core = TensorCore(rng.randn(2, 3, 2), indices=("r_0", "m_1", "r_1"))
+    phi = TensorCore(rng.randn(5, 3), indices=("batch", "m_1"))
+    out = TensorNetwork(cores=[core, phi], names=["core_0", "phi_0"]).contract(indices=("batch", "r_0", "r_1"))
+    np.testing.assert_allclose(np.asarray(out), np.einsum("amb,sm->sab", np.asarray(core), np.asarray(phi)), atol=1e-14)
+    assert out.indices == ("batch", "r_0", "r_1")
+    tn = TensorNetwork(cores=[phi.copy()], names=["phi_0"])
+    assert np.asarray(tn.sample(2)["phi_0"]).shape == (3,)
+    with pytest.raises(ValueError):
+        tn.add_core(phi.copy(), "phi_0")
+
+
+def test_stack_phis_layout():
+    from bsde_solver._inputs import stack_phis
+
+    x = np.random.RandomState(2).randn(7, 3)
+    phis = [O.poly_eval(x[:, i], 4) for i in range(3)]
+    out = stack_phis(phis)
+    assert out.shape == (3, 4, 7) and out.flags["C_CONTIGUOUS"]
+    np.testing.assert_array_equal(out[1, 2], x[:, 1] ** 2)
+    with pytest.raises(ValueError):
+        stack_phis([np.ones((7, 3)), np.ones((7, 4))])
+    with pytest.raises(ValueError):
+        stack_phis([np.ones((7, 3)), np.ones((6, 3))])
+
+
+def test_legendre_table_is_scipy_polyval_order():
+    from bsde_solver.core.calculus.basis import LegendreBasis
+
+    b = LegendreBasis(5)
+    asc = O.legendre_coefficients(5)
+    np.testing.assert_array_equal(b._coef()[:, :, ::-1], asc)      # descending (device Horner) == ascending reversed
+
+
+def test_solver_name_check_is_a_value_error():
+    from bsde_solver.core.optimisation.solve import solver_id
+
+    assert [solver_id(m) for m in ("lstsq", "lu", "qr", "solve")] == [0, 1, 2, 3]
+    with pytest.raises(ValueError, match="Unknown method"):
+        solver_id("cholesky")
+
+
+def test_hot_path_does_not_touch_tensor_network_contract(monkeypatch):
+    """ALS / fast_contract / multi_derivative go to the CUDA library, never through the host einsum utility."""
+    import inspect
+
+    from bsde_solver import utils
+    from bsde_solver.core.calculus import derivative
+    from bsde_solver.core.optimisation import als
+
+    for mod in (als, utils, derivative):
+        src = inspect.getsource(mod)
+        assert ".contract(" not in src, mod.__name__
