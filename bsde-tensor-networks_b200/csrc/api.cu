@@ -4,6 +4,7 @@
 #include "kernels.cuh"
 
 #include <dlfcn.h>
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -318,7 +319,15 @@ struct MicroCtx {
 };
 
 // assembly + (all-reduce) + solve/QR of core j; direction as MicroSolveArgs
-int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridge, const double* reg_diag, double* dbg) {
+struct SalsaReg {            // als.py:143-174, all device pointers
+    const double* eta = nullptr;
+    const double* gamma = nullptr;
+    const double* theta = nullptr;
+    int reg_left = 0, reg_right = 0;
+};
+
+int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridge, const double* reg_diag, double* dbg,
+               const SalsaReg* sr = nullptr) {
     const Train& T = *m.T;
     const int rl = T.ranks[j], rr = T.ranks[j + 1];
     const AsmPlan* P;
@@ -344,6 +353,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     if (direction > 0) { a.core_nb = T.core(j + 1); a.r_nb = T.ranks[j + 2]; }
     if (direction < 0) { a.core_nb = T.core(j - 1); a.r_nb = T.ranks[j - 1]; }
     a.ridge = ridge; a.reg_diag = reg_diag; a.dbg_A = dbg; a.info = m.info;
+    if (sr) { a.eta_ptr = sr->eta; a.gamma = sr->gamma; a.theta = sr->theta; a.reg_left = sr->reg_left; a.reg_right = sr->reg_right; }
     BSDE_TRY(launch_micro_solve(a, c->stream));
     c->launches++;
     prof_span(c, bsde_ctx::P_SOLVE, e3, prof_mark(c));
@@ -374,7 +384,7 @@ int als_sweep(bsde_ctx* c, const MicroCtx& m) {
 }
 
 int info_reset(bsde_ctx* c, int** info) {
-    BSDE_TRY(c->scalars.ensure(256));
+    BSDE_TRY(c->scalars.ensure(1024));      // one size for every user of this buffer: pointers into it must stay valid
     *info = c->scalars.as<int>() + 16;
     const int init[4] = {0, 0, 0, INT_MAX};
     BSDE_CUDA_OK(cudaMemcpyAsync(*info, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
@@ -442,6 +452,145 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
     if (info_host) {
         BSDE_CUDA_OK(cudaMemcpy(info_host, info, sizeof(int) * 4, cudaMemcpyDeviceToHost));
         if (info_host[3] == INT_MAX) info_host[3] = 0;
+    }
+    return 0;
+}
+
+
+// SALSA (als.py:99-323).  The host sequences the launches and mirrors the integer bookkeeping (sweep counters, bond
+// ranks); every number — SVDs, rank-adaptation test S[-1] > min_sv, regulariser, eta / omega / min_sv — is computed on
+// the device.  The only device->host traffic during a fit is the bond rank after a possible adaptation (one int).
+int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
+              const double* y_dev, int n_iter, int* ranks, const int* init_ranks, double omega, double freq_omega, double min_sv,
+              int max_rank, int solver_id, int do_reg, double* cores_host, int64_t cores_capacity, double* state_out_host) {
+    BSDE_TRY(check_ranks(d, p, ranks));
+    if (!init_ranks) return fail_msg(2, "fit_salsa: init_ranks is null");
+    if (!y_dev || !cores_host) return fail_msg(2, "fit_salsa: null y or cores pointer");
+    if (solver_id < 0 || solver_id > 3) return fail_msg(2, "Unknown method %d", solver_id);
+    if (n_iter < 0) return fail_msg(2, "fit_salsa: n_iter = %d", n_iter);
+    const int kRankLimit = 8;
+    // als.py:122-123 — caps from the ranks the train was CONSTRUCTED with; the bond left of core j reads max_ranks[j-1]
+    std::vector<int> max_ranks(d > 1 ? d - 1 : 1, 1);
+    for (int i = 0; i < d - 1; i++) max_ranks[i] = std::min(init_ranks[i] * p, max_rank);
+    if (d > 1) max_ranks[d - 2] = std::min(init_ranks[d] * p, max_rank);
+    std::vector<int> cap(d + 1, 1);
+    for (int k = 1; k < d; k++) {
+        if (ranks[k] > kRankLimit) return fail_msg(2, "SALSA supports ranks <= %d (bond %d has %d)", kRankLimit, k, ranks[k]);
+        cap[k] = std::max(ranks[k], std::min(max_ranks[k - 1], kRankLimit));
+    }
+    int64_t need = 0;
+    for (int j = 0; j < d; j++) need += (int64_t)cap[j] * p * cap[j + 1];
+    if (cores_capacity < need) return fail_msg(2, "fit_salsa: cores buffer holds %lld doubles, rank growth may need %lld", (long long)cores_capacity, (long long)need);
+
+    Inputs in;
+    BSDE_TRY(make_inputs(c, in, basis_kind, d, p, N, inputs_dev, nullptr, coef_host));
+    Train T;
+    BSDE_TRY(train_upload(c, T, d, p, ranks, cap.data(), cores_host));
+    int* info;
+    BSDE_TRY(info_reset(c, &info));
+    // device scalars: state = {eta, omega, min_sv}, residual sum, gamma[8], theta[8]; ints: adapted flag, new rank
+    BSDE_TRY(c->scalars.ensure(1024));
+    double* state = c->scalars.as<double>() + 32;
+    double* res_sum = state + 4;
+    double* gamma = state + 8;
+    double* theta = state + 24;
+    int* flags = c->scalars.as<int>() + 8;           // [0] adapted, [1] rank
+    const double init_state[3] = {1e-6, omega, min_sv};     // als.py:121
+    BSDE_CUDA_OK(cudaMemcpyAsync(state, init_state, sizeof init_state, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    double n_total = (double)N * c->world;           // shards are equal-sized up to one sample; exact count all-reduced below
+    if (c->world > 1) {
+        double cnt = (double)N;
+        BSDE_CUDA_OK(cudaMemcpyAsync(res_sum, &cnt, sizeof cnt, cudaMemcpyHostToDevice, c->stream));
+        BSDE_TRY(allreduce_moments(c, res_sum, 1));
+        BSDE_CUDA_OK(cudaMemcpyAsync(&cnt, res_sum, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+        BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+        n_total = cnt;
+    }
+
+    Bonds B;
+    BSDE_TRY(bonds_alloc(c, T, N, B));
+    const int rgrid = residual_grid(N);
+    BSDE_TRY(c->tmp.ensure(sizeof(double) * (rgrid + 8)));
+    MicroCtx m{&T, &in, &B, y_dev, solver_id, basis_kind == BASIS_POLY ? 1 : 0, info};
+
+    bool expand_rank = false, has_adapted = false;
+    const int warmup = 2;
+    int last_adapt = 0, rank_limited = 0;
+    for (int it = 0; it < n_iter; it++) {
+        if (it >= last_adapt + warmup) expand_rank = true;                               // als.py:224
+        if (has_adapted) { expand_rank = false; has_adapted = false; last_adapt = it; }   // als.py:225
+        if (d >= 2) {
+            BSDE_CUDA_OK(cudaMemcpyAsync(T.ranks_dev, T.ranks.data(), sizeof(int) * (d + 1), cudaMemcpyHostToDevice, c->stream));
+            BSDE_TRY(launch_orthonormalize_right(T.cores, T.off_dev, T.ranks_dev, p, d, 1, d - 1, c->stream));   // als.py:234
+            c->launches++;
+            BSDE_TRY(build_right(c, T, in, B, 2));          // bond[k] = R_{k-1} for k >= 2 (R_0 is rebuilt at j = 0)
+        }
+        for (int j = 0; j < d; j++) {
+            SalsaReg sr;
+            sr.eta = state;
+            if (j != 0) {
+                const int k = T.ranks[j];
+                const bool may_grow = expand_rank && k < max_ranks[j - 1];
+                if (may_grow && k >= kRankLimit) rank_limited = 1;
+                const int expand = (may_grow && k < kRankLimit) ? 1 : 0;
+                if (expand) BSDE_CUDA_OK(cudaMemsetAsync(flags, 0, 2 * sizeof(int), c->stream));
+                BSDE_TRY(launch_salsa_left(T.core(j - 1), T.core(j), T.ranks[j - 1], p, k, T.ranks[j + 1], state + 2, expand, do_reg,
+                                           gamma, flags + 1, flags, c->stream));
+                c->launches++;
+                if (expand) {
+                    int h[2];
+                    BSDE_CUDA_OK(cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+                    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+                    if (h[0]) { has_adapted = true; T.ranks[j] = h[1]; }
+                }
+                if (do_reg) { sr.gamma = gamma; sr.reg_left = 1; }
+                // L_j from the final core_{j-1}
+                BSDE_TRY(launch_interface_left(in, j - 1, T.core(j - 1), T.ranks[j - 1], T.ranks[j], j - 1 == 0 ? nullptr : B.at(j - 1),
+                                               B.at(j), c->stream));
+                c->launches++;
+            }
+            if (j != d - 1) {
+                BSDE_TRY(launch_salsa_right(T.core(j), T.core(j + 1), T.ranks[j], p, T.ranks[j + 1], T.ranks[j + 2], state + 2, do_reg,
+                                            theta, c->stream));
+                c->launches++;
+                if (do_reg) { sr.theta = theta; sr.reg_right = 1; }
+                // R_j from the moved core_{j+1}
+                BSDE_TRY(launch_interface_right(in, j + 1, T.core(j + 1), T.ranks[j + 1], T.ranks[j + 2],
+                                                j + 1 == d - 1 ? nullptr : B.at(j + 2), B.at(j + 1), c->stream));
+                c->launches++;
+            }
+            const double* Lj = j == 0 ? nullptr : B.at(j);
+            const double* Rj = j == d - 1 ? nullptr : B.at(j + 1);
+            if (j == 0 && it == 0) {                                                      // als.py:168-172
+                BSDE_TRY(launch_residual(in, j, T.core(j), T.ranks[j], T.ranks[j + 1], Lj, Rj, y_dev, nullptr, c->tmp.as<double>(),
+                                         res_sum, c->stream));
+                c->launches += 2;
+                BSDE_TRY(allreduce_moments(c, res_sum, 1));
+                BSDE_TRY(launch_salsa_scalars(state, res_sum, n_total, freq_omega, 0, c->stream));
+                c->launches++;
+            }
+            BSDE_TRY(micro_step(c, m, j, 0, 0.0, nullptr, nullptr, &sr));
+        }
+        // als.py:288-298 — residual of the last micro-step's design matrix with the new last core
+        {
+            const int j = d - 1;
+            BSDE_TRY(launch_residual(in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == 0 ? nullptr : B.at(j), nullptr, y_dev, nullptr,
+                                     c->tmp.as<double>(), res_sum, c->stream));
+            c->launches += 2;
+            BSDE_TRY(allreduce_moments(c, res_sum, 1));
+            BSDE_TRY(launch_salsa_scalars(state, res_sum, n_total, freq_omega, 1, c->stream));
+            c->launches++;
+        }
+    }
+    BSDE_TRY(train_download(c, T, cores_host));
+    for (int k = 0; k <= d; k++) ranks[k] = T.ranks[k];
+    if (state_out_host) {
+        BSDE_CUDA_OK(cudaMemcpy(state_out_host, state, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+        state_out_host[3] = rank_limited;
+        int hinfo[4];
+        BSDE_CUDA_OK(cudaMemcpy(hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
+        state_out_host[4] = hinfo[0]; state_out_host[5] = hinfo[1]; state_out_host[6] = hinfo[2];
     }
     return 0;
 }
@@ -639,7 +788,9 @@ int bsde_fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const d
                    double min_sv, int max_rank, int solver_id, int do_reg, double* cores_host, int64_t cores_capacity,
                    double* state_out_host) {
     BSDE_CHECK_CTX(c);
-    return fail_msg(5, "bsde_fit_salsa: not implemented yet");
+    Guard g(c);
+    return fit_salsa(c, basis_kind, d, p, N, inputs_dev, coef_host, y_dev, n_iter, ranks, init_ranks, omega, freq_omega, min_sv,
+                     max_rank, solver_id, do_reg, cores_host, cores_capacity, state_out_host);
 }
 
 int bsde_tt_eval(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,

@@ -120,6 +120,16 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
         if (row == col) {
             if (a.reg_diag) v += a.reg_diag[row];
             v += a.ridge;
+            if (a.eta_ptr) {
+                const double eta = *a.eta_ptr;
+                if (a.gamma && a.theta) {
+                    // Gamma term: index (a, i, k) of (r_l, p, r_r) -> gamma[a]^2.  Theta term: the reference flat-reshapes a
+                    // (r_r, p, r_l)^2 tensor, so the diagonal entry e carries theta[e / (p * r_l)]^2  (als.py:143-166)
+                    if (a.reg_left) { const double g = a.gamma[a1]; v += eta * eta * g * g; }
+                    if (a.reg_right) { const double t = a.theta[row / (a.p * a.rl)]; v += eta * eta * t * t; }
+                }
+                v += eta;
+            }
         }
         A[row * ld + col] = v;
     }

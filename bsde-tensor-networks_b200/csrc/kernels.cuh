@@ -58,8 +58,14 @@ struct MicroSolveArgs {
     double* core_j;          // (rl,p,rr) out
     double* core_nb;         // neighbour core: j+1 (rr, p, r_nb) for +1 ; j-1 (r_nb, p, rl) for -1
     int r_nb;                // the neighbour's far rank
-    double ridge;            // added to the diagonal (SALSA eta), 0 for ALS
-    const double* reg_diag;  // optional n-vector added to the diagonal (SALSA regulariser), may be null
+    double ridge;            // added to the diagonal, 0 for ALS
+    const double* reg_diag;  // optional n-vector added to the diagonal, may be null
+    // SALSA (als.py:143-174): A += eta^2 (Gamma^2 (x) I (x) I) [reg_left] + eta^2 (Theta-term, flat layout) [reg_right]
+    // + eta I, with eta read from device memory; the two regulariser terms only when gamma AND theta are given
+    const double* eta_ptr = nullptr;
+    const double* gamma = nullptr;
+    const double* theta = nullptr;
+    int reg_left = 0, reg_right = 0;
     double* dbg_A;           // optional n*n + n (A | b) dump for parity tests
     int* info;               // accumulated: [0] cholesky solves, [1] jacobi-svd solves, [2] lu solves, [3] min numerical rank
     const double* A_direct = nullptr;   // explicit n x n system (then rl = n, p = rr = 1 and moments is unused)
@@ -83,5 +89,13 @@ int launch_transpose(const double* src, int64_t rows, int64_t cols, double* dst,
 int launch_basis_eval(const Inputs& in, int deriv, double* out, cudaStream_t st);
 int mean_grid(int64_t N);
 int launch_block_sums(const double* v, int64_t N, double* partial, cudaStream_t st);
+
+
+// ---- salsa.cu ------------------------------------------------------------------------------------
+int launch_salsa_left(double* core_prev, double* core_cur, int rp, int p, int k, int rn, const double* min_sv, int expand,
+                      int do_reg, double* gamma, int* rank_out, int* adapted_out, cudaStream_t st);
+int launch_salsa_right(double* core_cur, double* core_next, int rl, int p, int k, int rn, const double* min_sv, int do_reg,
+                       double* theta, cudaStream_t st);
+int launch_salsa_scalars(double* state, const double* res_sum, double n_samples, double freq_omega, int mode, cudaStream_t st);
 
 }  // namespace bsde

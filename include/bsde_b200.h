@@ -97,9 +97,12 @@ BSDE_API int bsde_fit_als_host(bsde_ctx* ctx, int basis_kind, int d, int p, int6
                       double* cores_host, int* info_host);
 
 /* ---- SALSA   (replaces SALSA, core/optimisation/als.py:99-323) -------------------------------------------
- * ranks       : in = current bond ranks of cores_host; out = ranks after adaptation (d+1 ints)
- * init_ranks  : the ranks the TensorTrain object was constructed with (the reference's stale tt.ranks, als.py:122-123)
- * cores_host  : in/out, sized for the ranks it holds; cores_capacity = doubles available (>= what max_rank needs)
+ * ranks          : in = current bond ranks of cores_host; out = ranks after adaptation (d+1 ints)
+ * init_ranks     : the ranks the TensorTrain object was constructed with (the reference's stale tt.ranks, als.py:122-123)
+ * cores_host     : in/out, cores concatenated for the ranks they hold; cores_capacity = doubles available, at least
+ *                  sum_j cap_j * p * cap_{j+1} with cap_k = max(ranks[k], min(init_ranks[k-1]*p, max_rank, 8))
+ * state_out_host : optional double[8]: {eta, omega, min_sv, rank growth stopped by the kernel limit of 8 (0/1),
+ *                  cholesky solves, jacobi-svd solves, lu solves, unused}
  */
 BSDE_API int bsde_fit_salsa(bsde_ctx* ctx, int basis_kind, int d, int p, int64_t N, const double* inputs_dev,
                    const double* coef_host, const double* y_dev, int n_iter, int* ranks, const int* init_ranks,

@@ -226,3 +226,14 @@ def test_transpose_and_mean(backend):
     assert (backend.transpose(a, 1000, 7) == a.T).all()
     v = torch.randn(123457, dtype=torch.float64, device="cuda")
     assert abs(backend.mean(v) - v.mean().item()) < 1e-15
+
+
+def test_philox_stream_matches_the_restated_generator(backend):
+    """The device's counter-based increments against the numpy restatement of the same Philox4x32-10 + Box-Muller
+    stream: the integer part is exact, log / sincospi differ from numpy's by a few ulp."""
+    import oracle.tt_oracle as O
+
+    N, d, steps = 777, 3, 7
+    _, xi = backend.paths_simulate(1, np.array([1.0]), np.zeros(d), N, steps, 1.0, seed=(5 << 32) + 12345, sample_offset=1 << 33)
+    ref = O.philox_increments((5 << 32) + 12345, N, d, steps, sample_offset=1 << 33)
+    np.testing.assert_allclose(xi.cpu().numpy(), ref, rtol=0, atol=5e-15)
