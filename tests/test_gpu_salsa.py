@@ -140,3 +140,23 @@ def test_salsa_rank_growth_on_fresh_problem(backend):
     assert ranks.tolist() == [c.shape[0] for c in ref] + [1]
     assert max(ranks) > 1 and max(ranks) <= 3
     assert abs(rel(fit, y) - rel(O.tt_eval(ref, phis), y)) < 0.2 * rel(fit, y) + 1e-9
+
+
+def test_salsa_step0_identical_samples(backend):
+    """Time step 0 of the pipelines: every sample sits at X_0, the design matrix has rank one, the cores handed to the
+    SVD moves are rank deficient (singular values exactly 0).  The fit must stay finite and reproduce the oracle's
+    (ridge-shrunk) constant; SALSA is called with do_reg=False there (pipeline.py:135-136)."""
+    rng = np.random.RandomState(12)
+    N, d, p, r = 2000, 4, 3, 3
+    x = np.tile(np.array([0.0, 0.0, 0.0, 0.0]), (N, 1))
+    y = rng.randn(N) * 0.3 - 0.55
+    ranks0 = [1] + [r] * (d - 1) + [1]
+    init = [rng.rand(ranks0[i], p, ranks0[i + 1]) * 2 - 1 for i in range(d)]
+    phis = [O.poly_eval(x[:, i], p) for i in range(d)]
+    ref = O.salsa(phis, y, n_iter=4, ranks=ranks0, cores=[c.copy() for c in init], max_rank=3, randomize=False,
+                  init_ranks=ranks0, do_reg=False)
+    ref_fit = O.tt_eval(ref, phis)
+    cores, ranks, fit, state = _device_salsa(backend, x, y, p, init, 4, 3, ranks0, do_reg=False)
+    print("step-0 fit", fit[:2], "oracle", ref_fit[:2], "mean(y)", y.mean(), "state", state[:3])
+    assert np.isfinite(fit).all() and np.ptp(fit) < 1e-12
+    assert abs(fit[0] - ref_fit[0]) < 1e-6 * abs(ref_fit[0])
