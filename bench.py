@@ -212,9 +212,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    solve_paths = {}
+
     def fit_device():
         cores = init.copy()
-        be.fit_als(inp, y, N_SWEEPS, ranks, 0, cores)
+        info = be.fit_als(inp, y, N_SWEEPS, ranks, 0, cores)
+        solve_paths.update(cholesky=int(info[0]), jacobi_svd=int(info[1]), lu=int(info[2]), min_numerical_rank=int(info[3]))
         return cores
 
     sampler = ClockSampler(local)
@@ -275,6 +278,7 @@ def main():
     be.set_option("profile", 1)
     fit_device()
     stats = {k: (be.get_stat(f"{k}_ms"), int(be.get_stat(f"{k}_n"))) for k in ("assembly", "reduce", "allreduce", "solve", "interface")}
+    solve_phase_cycles = [be.get_stat(f"solve_phase{k}") for k in range(4)]
     be.set_option("profile", 0)
     asm_ms, asm_n = stats["assembly"]
     n_int, n_edge = R * P * R, P * R
@@ -290,7 +294,9 @@ def main():
                 "algorithmic_flops_per_launch": asm_flops_per_launch,
                 "note": "achieved counts the reference algorithm's n(n+1)+2n flops per sample; the kernel executes ~0.36x of them (Kronecker moment factorisation), so frac can exceed 1",
                 "share_of_step": {k: v[0] / total_prof for k, v in stats.items()},
-                "class_us_per_launch": {k: (1e3 * v[0] / v[1] if v[1] else None) for k, v in stats.items()}}
+                "class_us_per_launch": {k: (1e3 * v[0] / v[1] if v[1] else None) for k, v in stats.items()},
+                "solve_kernel_phase_cycles_per_launch": dict(zip(("expand_moments", "solve", "qr", "push_factor"),
+                                                                 [c / max(1, stats["solve"][1]) for c in solve_phase_cycles]))}
     try:
         with open(os.path.join(ROOT, "profiles", "assembly_traffic.json")) as f:
             roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
@@ -311,7 +317,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world) if N == N_PER_GPU else dict(workload_config(world), samples_per_gpu=N, workload="reduced-N debugging run (not the benchmark)"),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-            "fit_relative_residual": fit_quality,
+            "fit_relative_residual": fit_quality, "solves_per_fit": solve_paths,
         }))
     if world > 1:
         dist.destroy_process_group()

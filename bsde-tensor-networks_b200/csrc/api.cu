@@ -95,7 +95,7 @@ struct bsde_ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     int64_t launches = 0;
     int64_t use_graph = 1;
-    DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg;
+    DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg, clk;
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
     ncclComm_t comm = nullptr;
@@ -346,6 +346,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     if (c->world > 1) prof_span(c, bsde_ctx::P_ALLREDUCE, e2, e3);
     MicroSolveArgs a{};
     a.moments = c->moments.as<double>();
+    a.expand_map = P->d_expand;
     a.rl = rl; a.p = T.p; a.rr = rr; a.mono = m.mono; a.nLL = P->nLL; a.nRR = P->nRR; a.nB = P->nB;
     a.direction = direction; a.solver = m.solver;
     a.core_j = T.core(j);
@@ -353,6 +354,10 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     if (direction > 0) { a.core_nb = T.core(j + 1); a.r_nb = T.ranks[j + 2]; }
     if (direction < 0) { a.core_nb = T.core(j - 1); a.r_nb = T.ranks[j - 1]; }
     a.ridge = ridge; a.reg_diag = reg_diag; a.dbg_A = dbg; a.info = m.info;
+    if (c->profile && !c->capturing) {
+        if (!c->clk.p) { if (c->clk.ensure(64) == 0) cudaMemset(c->clk.p, 0, 64); }
+        a.clk = c->clk.as<long long>();
+    }
     if (sr) { a.eta_ptr = sr->eta; a.gamma = sr->gamma; a.theta = sr->theta; a.reg_left = sr->reg_left; a.reg_right = sr->reg_right; }
     BSDE_TRY(launch_micro_solve(a, c->stream));
     c->launches++;
@@ -668,6 +673,7 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     if (name && !strcmp(name, "profile")) {      // per-kernel-class event timing of eager launches; resets the counters
         c->profile = value;
         for (int k = 0; k < bsde_ctx::P_CLASSES; k++) { c->prof_ms[k] = 0.0; c->prof_n[k] = 0; }
+        if (c->clk.p) cudaMemset(c->clk.p, 0, 64);
         return 0;
     }
     return fail_msg(2, "unknown option '%s'", name ? name : "(null)");
@@ -683,6 +689,12 @@ int bsde_ctx_get_stat(bsde_ctx* c, const char* name, double* out) {
             if (!strcmp(name + n, "_ms")) { *out = c->prof_ms[k]; return 0; }
             if (!strcmp(name + n, "_n")) { *out = (double)c->prof_n[k]; return 0; }
         }
+    }
+    if (!strncmp(name, "solve_phase", 11) && name[11] >= '0' && name[11] <= '3' && !name[12]) {
+        long long v[4] = {0, 0, 0, 0};
+        if (c->clk.p) BSDE_CUDA_OK(cudaMemcpy(v, c->clk.p, sizeof v, cudaMemcpyDeviceToHost));
+        *out = (double)v[name[11] - '0'];
+        return 0;
     }
     if (!strcmp(name, "sm_count")) { *out = c->sm_count; return 0; }
     if (!strcmp(name, "workspace_bytes")) {

@@ -190,13 +190,15 @@ __device__ __forceinline__ void write_partials(const AsmArgs& a, double* sm, dou
 // register-blocked variant
 // =====================================================================================================
 // shared table (uint16 function indices, premultiplied by kStride on load):
-//   rows1 [RT1][8][2] = (basis function, LL function)      cols1 [CT1][8] = RR function
-//   rows2 [RT2][8][2] = (phi*y function, L function)        cols2 [8]      = R function
+//   rows1 [RT1][8][2] = two staged functions whose product is the A fragment of M1, cols1 [CT1][8] = its B fragment
+//   rows2 [RT2][8][2] / cols2 [8] = the same for M2                 (which functions: see asm_plan_build's layouts)
+// resident CTAs per SM the register allocation is tuned for: 3 (168 registers).  With 4 (128 registers) the operand
+// look-ahead spills and the kernel is 30 % slower (measured at both 15 and 20 accumulator tiles).
 #ifndef BSDE_RB_MIN_BLOCKS
-#define BSDE_RB_MIN_BLOCKS 3
+#define BSDE_RB_MIN_BLOCKS(nt) 3
 #endif
 template <int RT1, int CT1, int RT2, int RB, int PB>
-__global__ void __launch_bounds__(kAsmThreads, BSDE_RB_MIN_BLOCKS)
+__global__ void __launch_bounds__(kAsmThreads, BSDE_RB_MIN_BLOCKS(RT1 * CT1 + RT2))
 k_assemble_rb(AsmArgs a) {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -396,8 +398,10 @@ int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, i
         switch (P.rb_class) {
             case 0: return run_kernel(k_assemble_rb<1, 1, 1, RB, PB>, op, P, a, st, occ);
             case 1: return run_kernel(k_assemble_rb<2, 1, 1, RB, PB>, op, P, a, st, occ);
-            case 2: return run_kernel(k_assemble_rb<4, 1, 2, RB, PB>, op, P, a, st, occ);
-            case 3: return run_kernel(k_assemble_rb<2, 2, 1, RB, PB>, op, P, a, st, occ);
+            case 2: return run_kernel(k_assemble_rb<2, 2, 1, RB, PB>, op, P, a, st, occ);
+            case 3: return run_kernel(k_assemble_rb<4, 1, 2, RB, PB>, op, P, a, st, occ);
+            case 4: return run_kernel(k_assemble_rb<5, 1, 2, RB, PB>, op, P, a, st, occ);
+            case 5: return run_kernel(k_assemble_rb<13, 1, 2, RB, PB>, op, P, a, st, occ);
             default: return run_kernel(k_assemble_rb<9, 2, 2, RB, PB>, op, P, a, st, occ);
         }
     }
@@ -414,7 +418,9 @@ int dispatch(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* o
 }
 
 // tile-count classes of the register-blocked kernel: (row tiles of M1, column tiles of M1, row tiles of M2)
-const int kRbClasses[5][3] = {{1, 1, 1}, {2, 1, 1}, {4, 1, 2}, {2, 2, 1}, {9, 2, 2}};
+// ordered by total tile count RT1*CT1 + RT2
+constexpr int kNumRbClasses = 7;
+const int kRbClasses[kNumRbClasses][3] = {{1, 1, 1}, {2, 1, 1}, {2, 2, 1}, {4, 1, 2}, {5, 1, 2}, {13, 1, 2}, {9, 2, 2}};
 
 }  // namespace
 
@@ -440,13 +446,27 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
     size_t tab_smem = 0;
     int n_tiles = 0;
 
-    // ---- register-blocked layout: rows (beta, lambda), columns rho; M2 rows (m, a), columns b ----
-    const int rows1 = P.nB * P.nLL, rows2 = p * rl;
-    const int needRT1 = (rows1 + 7) / 8, needCT1 = (P.nRR + 7) / 8, needRT2 = (rows2 + 7) / 8;
+    // ---- register-blocked layouts (k_assemble_rb: A fragment = product of two staged functions, B fragment = one) ----
+    //   layout 0: M1 rows (beta, lambda), columns rho;     M2 rows (m, a), columns b
+    //   layout 1: M1 rows (lambda, rho),  columns beta;    M2 rows (a, b), columns m      (15 tiles at r = p = 4)
+    // The layout and tile-count class with the fewest DMMA tiles is chosen.
     P.rb_class = -1;
-    if (!force_generic)
-        for (int k = 0; k < 5; k++)
-            if (needRT1 <= kRbClasses[k][0] && needCT1 <= kRbClasses[k][1] && needRT2 <= kRbClasses[k][2]) { P.rb_class = k; break; }
+    int layout = 0;
+    if (!force_generic) {
+        int best_tiles = 1 << 30;
+        for (int lay = 0; lay < 2; lay++) {
+            const int rows1 = lay == 0 ? P.nB * P.nLL : P.nLL * P.nRR, cols1 = lay == 0 ? P.nRR : P.nB;
+            const int rows2 = lay == 0 ? p * rl : rl * rr, cols2 = lay == 0 ? rr : p;
+            if (cols2 > 8) continue;
+            const int needRT1 = (rows1 + 7) / 8, needCT1 = (cols1 + 7) / 8, needRT2 = (rows2 + 7) / 8;
+            for (int k = 0; k < kNumRbClasses; k++)
+                if (needRT1 <= kRbClasses[k][0] && needCT1 <= kRbClasses[k][1] && needRT2 <= kRbClasses[k][2]) {
+                    const int tiles = kRbClasses[k][0] * kRbClasses[k][1] + kRbClasses[k][2];
+                    if (tiles < best_tiles) { best_tiles = tiles; P.rb_class = k; layout = lay; }
+                    break;
+                }
+        }
+    }
 
     if (P.rb_class >= 0) {
         const int RT1 = kRbClasses[P.rb_class][0], CT1 = kRbClasses[P.rb_class][1], RT2 = kRbClasses[P.rb_class][2];
@@ -454,31 +474,35 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
         P.NJ = n_tiles; P.n_groups = 1; P.n_jobs = n_tiles;
         tab.assign((size_t)RT1 * 16 + CT1 * 8 + RT2 * 16 + 8, 0);
         uint16_t* t = tab.data();
-        for (int r = 0; r < RT1 * 8; r++)
-            if (r < rows1) { t[r * 2] = (uint16_t)(P.fRow1 + r / P.nLL); t[r * 2 + 1] = (uint16_t)(P.fLL + r % P.nLL); }
-        t += RT1 * 16;
-        for (int c = 0; c < CT1 * 8; c++) t[c] = (uint16_t)(c < P.nRR ? P.fRR + c : 0);
-        t += CT1 * 8;
-        for (int r = 0; r < RT2 * 8; r++)
-            if (r < rows2) { t[r * 2] = (uint16_t)(P.fRow2 + r / rl); t[r * 2 + 1] = (uint16_t)(P.fL + r % rl); }
-        t += RT2 * 16;
-        for (int c = 0; c < 8; c++) t[c] = (uint16_t)(c < rr ? P.fR + c : 0);
-        P.tab_entries = (int)tab.size();
-        tab_smem = tab.size() * sizeof(uint16_t);
+        uint16_t* rows1t = t;
+        uint16_t* cols1t = rows1t + RT1 * 16;
+        uint16_t* rows2t = cols1t + CT1 * 8;
+        uint16_t* cols2t = rows2t + RT2 * 16;
+        // row index of an M1 / M2 entry and its column, per layout
+        auto row1 = [&](int beta, int lam, int rho) { return layout == 0 ? beta * P.nLL + lam : lam * P.nRR + rho; };
+        auto col1 = [&](int beta, int lam, int rho) { (void)lam; return layout == 0 ? rho : beta; };
+        auto row2 = [&](int m, int a, int b) { return layout == 0 ? m * rl + a : a * rr + b; };
+        auto col2 = [&](int m, int a, int b) { (void)a; return layout == 0 ? b : m; };
         for (int beta = 0; beta < P.nB; beta++)
             for (int lam = 0; lam < P.nLL; lam++)
                 for (int rho = 0; rho < P.nRR; rho++) {
-                    const int row = beta * P.nLL + lam;
-                    const int tile = (row / 8) * CT1 + rho / 8;
-                    P.h_gather[((size_t)beta * P.nLL + lam) * P.nRR + rho] = tile * 64 + (row % 8) * 8 + rho % 8;
+                    const int r = row1(beta, lam, rho), c = col1(beta, lam, rho);
+                    rows1t[r * 2] = (uint16_t)(layout == 0 ? P.fRow1 + beta : P.fLL + lam);
+                    rows1t[r * 2 + 1] = (uint16_t)(layout == 0 ? P.fLL + lam : P.fRR + rho);
+                    cols1t[c] = (uint16_t)(layout == 0 ? P.fRR + rho : P.fRow1 + beta);
+                    P.h_gather[((size_t)beta * P.nLL + lam) * P.nRR + rho] = ((r / 8) * CT1 + c / 8) * 64 + (r % 8) * 8 + c % 8;
                 }
         for (int m = 0; m < p; m++)
             for (int a = 0; a < rl; a++)
                 for (int b = 0; b < rr; b++) {
-                    const int row = m * rl + a;
-                    const int tile = RT1 * CT1 + row / 8;
-                    P.h_gather[base2 + ((size_t)m * rl + a) * rr + b] = tile * 64 + (row % 8) * 8 + b;
+                    const int r = row2(m, a, b), c = col2(m, a, b);
+                    rows2t[r * 2] = (uint16_t)(layout == 0 ? P.fRow2 + m : P.fL + a);
+                    rows2t[r * 2 + 1] = (uint16_t)(layout == 0 ? P.fL + a : P.fR + b);
+                    cols2t[c] = (uint16_t)(layout == 0 ? P.fR + b : P.fRow2 + m);
+                    P.h_gather[base2 + ((size_t)m * rl + a) * rr + b] = (RT1 * CT1 + r / 8) * 64 + (r % 8) * 8 + c;
                 }
+        P.tab_entries = (int)tab.size();
+        tab_smem = tab.size() * sizeof(uint16_t);
     } else {
         // ---- generic layout: rows beta, columns (lambda, rho) pairs; M2 rows m, columns (a, b) ----
         struct Col { int f1, f2, key1, key2; };
@@ -548,6 +572,24 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
     if (per_sm > 6) per_sm = 6;
     P.grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count * per_sm));
 
+    {   // expansion map of the solve kernel: entry of A / b -> canonical moment
+        auto pair_index = [](int a, int b, int r) { if (a > b) std::swap(a, b); return a * r - (a * (a - 1)) / 2 + (b - a); };
+        const int n = P.n;
+        std::vector<uint16_t> emap((size_t)n * n + n);
+        for (int row = 0; row < n; row++) {
+            const int a1 = row / (p * rr), m1 = (row / rr) % p, b1 = row % rr;
+            for (int col = 0; col < n; col++) {
+                const int a2 = col / (p * rr), m2 = (col / rr) % p, b2 = col % rr;
+                const int lam = pair_index(a1, a2, rl), rho = pair_index(b1, b2, rr);
+                const int beta = mono ? (m1 + m2) : pair_index(m1, m2, p);
+                emap[(size_t)row * n + col] = (uint16_t)((beta * P.nLL + lam) * P.nRR + rho);
+            }
+            emap[(size_t)n * n + row] = (uint16_t)(base2 + (m1 * rl + a1) * rr + b1);
+        }
+        if (P.n_mom > 65535) return fail_msg(2, "assembly: %d moments exceed the 16-bit expansion map", P.n_mom);
+        BSDE_CUDA_OK(cudaMalloc(&P.d_expand, emap.size() * sizeof(uint16_t)));
+        BSDE_CUDA_OK(cudaMemcpy(P.d_expand, emap.data(), emap.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     BSDE_CUDA_OK(cudaMalloc(&P.d_tab, tab.size() * sizeof(uint16_t)));
     BSDE_CUDA_OK(cudaMalloc(&P.d_gather, P.h_gather.size() * sizeof(int32_t)));
     BSDE_CUDA_OK(cudaMemcpy(P.d_tab, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
@@ -558,7 +600,8 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
 void asm_plan_free(AsmPlan& P) {
     if (P.d_tab) cudaFree(P.d_tab);
     if (P.d_gather) cudaFree(P.d_gather);
-    P.d_tab = nullptr; P.d_gather = nullptr;
+    if (P.d_expand) cudaFree(P.d_expand);
+    P.d_tab = nullptr; P.d_gather = nullptr; P.d_expand = nullptr;
 }
 
 int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, const double* R, const double* y,

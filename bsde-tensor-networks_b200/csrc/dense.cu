@@ -100,23 +100,24 @@ struct SolveScratch {
     double* red;    // n  scratch
 };
 
-__device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int ld, double* bvec) {
+__device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int ld, double* bvec, double* stage) {
     const int n = a.rl * a.p * a.rr;
     if (a.A_direct) {    // bsde_solve: an explicit system instead of moments (rl = n, p = rr = 1)
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) A[(e / n) * ld + (e % n)] = a.A_direct[e];
         for (int e = threadIdx.x; e < n; e += blockDim.x) bvec[e] = a.b_direct[e];
         return;
     }
-    const double* M1 = a.moments;
-    const double* M2 = a.moments + (size_t)a.nB * a.nLL * a.nRR;
+    // stage the moments in shared memory with coalesced loads (the gather below would otherwise pay one L2 round trip
+    // per entry); `stage` is the V / scratch area that is free until the solve starts
+    const int n_m1 = a.nB * a.nLL * a.nRR, n_mom = n_m1 + n;
+    for (int e = threadIdx.x; e < n_mom; e += blockDim.x) stage[e] = a.moments[e];
+    __syncthreads();
+    // a.expand_map[e] (built once per core shape on the host, assembly.cu) = index of the moment that entry e of the
+    // row-major A (then of b) is equal to: A[(a,m,b),(a',m',b')] = M1[beta(m,m')][lambda(a,a')][rho(b,b')]
+    const uint16_t* map = a.expand_map;
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-        const int row = e / n, col = e % n;
-        const int a1 = row / (a.p * a.rr), m1 = (row / a.rr) % a.p, b1 = row % a.rr;
-        const int a2 = col / (a.p * a.rr), m2 = (col / a.rr) % a.p, b2 = col % a.rr;
-        const int lam = pair_index(min(a1, a2), max(a1, a2), a.rl);
-        const int rho = pair_index(min(b1, b2), max(b1, b2), a.rr);
-        const int beta = a.mono ? (m1 + m2) : pair_index(min(m1, m2), max(m1, m2), a.p);
-        double v = M1[((size_t)beta * a.nLL + lam) * a.nRR + rho];
+        const int row = e / n, col = e - row * n;
+        double v = stage[map[e]];
         if (row == col) {
             if (a.reg_diag) v += a.reg_diag[row];
             v += a.ridge;
@@ -125,7 +126,7 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
                 if (a.gamma && a.theta) {
                     // Gamma term: index (a, i, k) of (r_l, p, r_r) -> gamma[a]^2.  Theta term: the reference flat-reshapes a
                     // (r_r, p, r_l)^2 tensor, so the diagonal entry e carries theta[e / (p * r_l)]^2  (als.py:143-166)
-                    if (a.reg_left) { const double g = a.gamma[a1]; v += eta * eta * g * g; }
+                    if (a.reg_left) { const double g = a.gamma[row / (a.p * a.rr)]; v += eta * eta * g * g; }
                     if (a.reg_right) { const double t = a.theta[row / (a.p * a.rl)]; v += eta * eta * t * t; }
                 }
                 v += eta;
@@ -133,17 +134,13 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
         }
         A[row * ld + col] = v;
     }
-    for (int row = threadIdx.x; row < n; row += blockDim.x) {
-        const int a1 = row / (a.p * a.rr), m1 = (row / a.rr) % a.p, b1 = row % a.rr;
-        const double v = M2[((size_t)m1 * a.rl + a1) * a.rr + b1];
-        bvec[row] = v;
-    }
+    for (int row = threadIdx.x; row < n; row += blockDim.x) bvec[row] = stage[map[n * n + row]];
 }
 
 // Named barrier for the first `count` threads of the CTA (the fast path runs on 8 of the 32 warps).
-__device__ __forceinline__ void bar_sub(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sub(int) { __syncthreads(); }
 
-constexpr int kCholThreads = 256;
+constexpr int kCholThreads = 1024;  // the factorisation uses the whole CTA: <= 4 trailing entries per thread and column
 constexpr double kGateSafety = 100.0;
 
 // Fast path of 'lstsq', executed by threads 0..255: equilibrated Cholesky of A with two right-hand sides carried
@@ -182,31 +179,65 @@ __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_r
         else if (j <= i) A[i * ld + j] *= S.sc[i] * S.sc[j];
     }
     bar_sub(kCholThreads);
-    const int ty = tid >> 4, tx = tid & 15;
-    for (int k = 0; k < n; k++) {
-        const double piv = A[k * ld + k];
-        if (!(piv > 0.0)) return false;                       // uniform: every thread reads the same value
-        const double inv = rsqrt(piv);
-        bar_sub(kCholThreads);
-        for (int i = k + 1 + tid; i <= n + 1; i += kCholThreads) A[i * ld + k] *= inv;
-        if (tid == 0) A[k * ld + k] = inv;                    // keep the reciprocal of the factor's diagonal
-        bar_sub(kCholThreads);
-        for (int i = k + 1 + ty; i <= n + 1; i += 16) {
-            const double lik = A[i * ld + k];
+    // Right-looking factorisation, two columns per trailing update (rank-2) and the column scaling folded into the
+    // update and the back substitution (stored column k = L_ik / dinv_k).  FP64 has ~75 cycles of dependent-issue
+    // latency on this part (bench/micro/chol64.cu), so the cost is the number of dependent FP64 operations and block
+    // barriers per pivot: every thread recomputes the 2x2 pivot block redundantly instead of waiting for a broadcast.
+    const int ty = tid >> 5, tx = tid & 31;
+    double* dinv = S.red;                                     // 1 / sqrt(pivot_k)
+    int k = 0;
+    for (; k + 1 < n; k += 2) {
+        const double p0 = A[k * ld + k];
+        if (!(p0 > 0.0)) return false;                        // uniform: every thread reads the same values
+        const double r0 = rsqrt(p0), i0 = r0 * r0;
+        const double a10 = A[(k + 1) * ld + k];
+        const double p1 = fma(-a10 * i0, a10, A[(k + 1) * ld + k + 1]);
+        if (!(p1 > 0.0)) return false;
+        const double r1 = rsqrt(p1), i1 = r1 * r1;
+        if (tid == 0) { dinv[k] = r0; dinv[k + 1] = r1; }
+        for (int i = k + 2 + ty; i <= n + 1; i += 32) {
+            const double ui = A[i * ld + k];
+            const double vi = fma(-ui * i0, a10, A[i * ld + k + 1]);
+            const double li0 = ui * i0, li1 = vi * i1;
             const int jmax = (i < n) ? i : n - 1;
-            for (int j = k + 1 + tx; j <= jmax; j += 16) A[i * ld + j] = fma(-lik, A[j * ld + k], A[i * ld + j]);
+            for (int j = k + 2 + tx; j <= jmax; j += 32) {
+                const double uj = A[j * ld + k];
+                const double vj = fma(-uj * i0, a10, A[j * ld + k + 1]);
+                A[i * ld + j] = fma(-li1, vj, fma(-li0, uj, A[i * ld + j]));
+            }
+        }
+        bar_sub(kCholThreads);
+        // column k+1 of the panel in its updated (unscaled) form, needed by the back substitution
+        for (int i = k + 2 + tid; i <= n + 1; i += kCholThreads) A[i * ld + k + 1] = fma(-A[i * ld + k] * i0, a10, A[i * ld + k + 1]);
+        if (tid == 0) A[(k + 1) * ld + k + 1] = p1;
+        bar_sub(kCholThreads);
+    }
+    if (k < n) {                                              // odd n: last column on its own
+        const double piv = A[k * ld + k];
+        if (!(piv > 0.0)) return false;
+        const double r = rsqrt(piv), ipiv = r * r;
+        if (tid == 0) dinv[k] = r;
+        for (int i = k + 1 + ty; i <= n + 1; i += 32) {
+            const double lik = A[i * ld + k] * ipiv;
+            const int jmax = (i < n) ? i : n - 1;
+            for (int j = k + 1 + tx; j <= jmax; j += 32) A[i * ld + j] = fma(-lik, A[j * ld + k], A[i * ld + j]);
         }
         bar_sub(kCholThreads);
     }
-    // back substitution L^T x = z for both right-hand sides: warp 0 -> b, warp 1 -> probe
+    // back substitution L^T x = z for both right-hand sides: warp 0 -> b, warp 1 -> probe.
+    // Stored column k holds L_ik * sqrt(pivot_k) (unscaled), rows n / n+1 hold z_k * sqrt(pivot_k).
     if (tid < 64) {
         const int lane = tid & 31;
         double* z = A + (n + (tid >> 5)) * ld;
+        for (int i = lane; i < n; i += 32) z[i] *= dinv[i];                   // z_k
+        __syncwarp();
         for (int k = n - 1; k >= 0; k--) {
-            const double xk = z[k] * A[k * ld + k];
+            const double dk = dinv[k];
+            const double xk = z[k] * dk;                                        // x_k = z_k / L_kk
             __syncwarp();
             if (lane == 0) z[k] = xk;
-            for (int i = lane; i < k; i += 32) z[i] = fma(-A[k * ld + i], xk, z[i]);
+            // L_ki = A[k][i] * dinv_i  (row k, i < k)
+            for (int i = lane; i < k; i += 32) z[i] = fma(-A[k * ld + i] * dinv[i], xk, z[i]);
             __syncwarp();
         }
         if (tid < 32) {
@@ -230,16 +261,35 @@ __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_r
 __device__ int jacobi_lstsq(SolveScratch& S, int n, const double* bvec, double* xout) {
     double* G = S.G;
     double* V = S.V;
+    double* cn = S.sc;            // squared column norms at the start of the sweep (for the negligible-column test)
     __shared__ int s_rot;
-    __shared__ double s_smax;
+    __shared__ double s_smax, s_nmax;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) V[e] = ((e / n) == (e % n)) ? 1.0 : 0.0;
     __syncthreads();
     const int m = (n + 1) & ~1;
     const double tol = DBL_EPSILON * sqrt((double)n);
     for (int sweep = 0; sweep < 40; sweep++) {
+        for (int c = warp; c < n; c += nwarps) {
+            const double* g = G + (size_t)c * n;
+            double ss = 0.0;
+            for (int i = lane; i < n; i += 32) ss = fma(g[i], g[i], ss);
+            ss = warp_sum(ss);
+            if (lane == 0) cn[c] = ss;
+        }
         if (threadIdx.x == 0) s_rot = 0;
         __syncthreads();
+        if (threadIdx.x < 32) {
+            double mx = 0.0;
+            for (int c = lane; c < n; c += 32) mx = fmax(mx, cn[c]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) s_nmax = mx;
+        }
+        __syncthreads();
+        // columns whose norm is far below the truncation cutoff (eps*n*s_max) carry only rounding noise: rotating them
+        // never converges in a relative sense and they are dropped from the solution anyway
+        const double negligible = 1e-4 * (DBL_EPSILON * n) * (DBL_EPSILON * n) * s_nmax;
         for (int step = 0; step < m - 1; step++) {
             for (int k = warp; k < m / 2; k += nwarps) {
                 int p, q;
@@ -247,6 +297,7 @@ __device__ int jacobi_lstsq(SolveScratch& S, int n, const double* bvec, double* 
                 else { p = (step + k) % (m - 1); q = (step - k + m - 1) % (m - 1); }
                 if (p > q) { const int t = p; p = q; q = t; }
                 if (q >= n) continue;
+                if (cn[p] <= negligible || cn[q] <= negligible) continue;     // cn: norms at the start of the sweep
                 double* gp = G + (size_t)p * n;
                 double* gq = G + (size_t)q * n;
                 double al = 0.0, be = 0.0, ga = 0.0;
@@ -350,9 +401,20 @@ __device__ void lu_solve(SolveScratch& S, int n, double* xout) {
     __syncthreads();
 }
 
+// phase timing (option "profile"): thread 0 accumulates clock64() deltas per phase into a.clk[phase]
+#define BSDE_PHASE(idx)                                                                              \
+    do {                                                                                             \
+        if (a.clk && threadIdx.x == 0) {                                                             \
+            const long long _now = clock64();                                                        \
+            atomicAdd((unsigned long long*)(a.clk + (idx)), (unsigned long long)(_now - t_phase));   \
+            t_phase = _now;                                                                          \
+        }                                                                                            \
+    } while (0)
+
 __global__ void __launch_bounds__(kDenseThreads)
 k_micro_solve(MicroSolveArgs a) {
     extern __shared__ double sm[];
+    long long t_phase = a.clk ? clock64() : 0;
     const int n = a.rl * a.p * a.rr;
     const int ld = n + 1;
     SolveScratch S;
@@ -370,22 +432,23 @@ k_micro_solve(MicroSolveArgs a) {
     __shared__ int s_path, s_rank, s_ok;
     __shared__ double s_red[4];
 
-    expand_normal_equations(a, S.A, ld, S.bvec);
+    expand_normal_equations(a, S.A, ld, S.bvec, S.V);
     __syncthreads();
+    BSDE_PHASE(0);
     if (a.dbg_A) {
         for (int e = threadIdx.x; e < n * n; e += blockDim.x) a.dbg_A[e] = S.A[(e / n) * ld + (e % n)];
         for (int e = threadIdx.x; e < n; e += blockDim.x) a.dbg_A[n * n + e] = S.bvec[e];
     }
     __syncthreads();
     if (a.solver == SOLVER_LSTSQ) {
-        if (threadIdx.x < kCholThreads) {
+        {
             const bool ok = cholesky_solve(S, n, S.x, s_red);
             if (threadIdx.x == 0) { s_ok = ok ? 1 : 0; s_path = ok ? 0 : 1; s_rank = n; }
         }
         __syncthreads();
         if (!s_ok) {
             // rebuild A (column-major == row-major, A is symmetric) with ld = n for the Jacobi path
-            expand_normal_equations(a, S.G, n, S.bvec);
+            expand_normal_equations(a, S.G, n, S.bvec, S.V);
             __syncthreads();
             double* xtmp = S.red;
             const int rank = jacobi_lstsq(S, n, S.bvec, xtmp);
@@ -398,6 +461,7 @@ k_micro_solve(MicroSolveArgs a) {
         if (threadIdx.x == 0) { s_path = 2; s_rank = n; }
     }
     __syncthreads();
+    BSDE_PHASE(1);
     if (threadIdx.x == 0 && a.info) {          // counters: [0] cholesky, [1] jacobi, [2] lu, [3] min numerical rank
         a.info[s_path] += 1;
         if (s_rank < a.info[3]) a.info[3] = s_rank;
@@ -415,6 +479,7 @@ k_micro_solve(MicroSolveArgs a) {
         __syncthreads();
         if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
         __syncthreads();
+        BSDE_PHASE(2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) a.core_j[i] = Mq[i];
         // core_{j+1} <- S @ right_unfold(core_{j+1})   (rr x (p*r_nb))
         const int cols = a.p * a.r_nb;
@@ -435,6 +500,7 @@ k_micro_solve(MicroSolveArgs a) {
         __syncthreads();
         if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
         __syncthreads();
+        BSDE_PHASE(2);
         for (int e = threadIdx.x; e < n; e += blockDim.x) {   // core_j = Q^T
             const int c = e / mrows, r = e % mrows;
             a.core_j[e] = Mq[r * k + c];
@@ -450,6 +516,7 @@ k_micro_solve(MicroSolveArgs a) {
         __syncthreads();
         for (int e = threadIdx.x; e < rows * k; e += blockDim.x) a.core_nb[e] = W[e];
     }
+    BSDE_PHASE(3);
 }
 
 // Whole-train orthonormalisation by successive QRs (tensor_train.py:34-87), one CTA, cores in global memory.

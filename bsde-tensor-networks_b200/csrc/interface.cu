@@ -16,12 +16,25 @@ namespace bsde {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kSB = 2;          // samples carried per thread by the interface kernels
 
 inline int grid_for(int64_t N) {
     int64_t b = (N + kThreads - 1) / kThreads;
     const int64_t cap = 148 * 16;
     return (int)(b < cap ? b : cap);
 }
+
+// interface kernels: kSB samples per thread, CTAs a multiple of the SM count when the batch is large
+inline int grid_for_blocked(int64_t N) {
+    int64_t b = (N + (int64_t)kThreads * kSB - 1) / ((int64_t)kThreads * kSB);
+    const int64_t cap = 148 * 16;
+    if (b >= 148) b = (b / 148) * 148;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+// Each thread carries kSB samples (a block apart, so every load instruction stays coalesced across the warp): one
+// broadcast shared-memory read of a core entry then feeds kSB FMAs.  With one sample per thread the kernels were
+// bound by the issue rate of those reads (64 LDS per sample at r = p = 4), at 43 % of HBM bandwidth.
 
 template <int RB, int PB>
 __global__ void __launch_bounds__(kThreads)
@@ -32,28 +45,56 @@ k_interface_left(Inputs in, int j, const double* __restrict__ core, int r_in, in
     for (int i = threadIdx.x; i < r_in * p * r_out; i += blockDim.x) csm[i] = core[i];
     __syncthreads();
     const int64_t N = in.N;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
-        double phi[PB];
-        basis_values<PB>(in, j, s, 0, phi);
-        double acc[RB];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s0 < N; s0 += stride * kSB) {
+        double phi[kSB][PB], acc[kSB][RB], lall[kSB][RB];
+        int64_t sidx[kSB];
+        // all global loads of the chunk are issued before the first use (ncu: 53 % long_scoreboard stalls with the
+        // load inside the rank loop): first the interface components, then the inputs of the basis
 #pragma unroll
-        for (int b = 0; b < RB; b++) acc[b] = 0.0;
-        for (int a = 0; a < r_in; a++) {
-            const double la = Lin ? Lin[(int64_t)a * N + s] : 1.0;
+        for (int u = 0; u < kSB; u++) {
+            const int64_t s = s0 + u * stride;
+            sidx[u] = s < N ? s : N - 1;                 // clamped duplicates are computed and not stored
+        }
+#pragma unroll
+        for (int a = 0; a < RB; a++)
+#pragma unroll
+            for (int u = 0; u < kSB; u++) lall[u][a] = (a < r_in) ? (Lin ? Lin[(int64_t)a * N + sidx[u]] : 1.0) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kSB; u++) {
+            basis_values<PB>(in, j, sidx[u], 0, phi[u]);
+#pragma unroll
+            for (int b = 0; b < RB; b++) acc[u][b] = 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < RB; a++) {
+            if (a >= r_in) break;
 #pragma unroll
             for (int m = 0; m < PB; m++) {
                 if (m < p) {
-                    const double t = la * phi[m];
                     const double* c = csm + (a * p + m) * r_out;
+                    double t[kSB];
+#pragma unroll
+                    for (int u = 0; u < kSB; u++) t[u] = lall[u][a] * phi[u][m];
 #pragma unroll
                     for (int b = 0; b < RB; b++)
-                        if (b < r_out) acc[b] = fma(t, c[b], acc[b]);
+                        if (b < r_out) {
+                            const double cb = c[b];
+#pragma unroll
+                            for (int u = 0; u < kSB; u++) acc[u][b] = fma(t[u], cb, acc[u][b]);
+                        }
                 }
             }
         }
 #pragma unroll
-        for (int b = 0; b < RB; b++)
-            if (b < r_out) Lout[(int64_t)b * N + s] = acc[b];
+        for (int u = 0; u < kSB; u++) {
+            const int64_t s = s0 + u * stride;
+            if (s < N) {
+#pragma unroll
+                for (int b = 0; b < RB; b++)
+                    if (b < r_out) Lout[(int64_t)b * N + s] = acc[u][b];
+            }
+        }
     }
 }
 
@@ -67,26 +108,46 @@ k_interface_right(Inputs in, int j, const double* __restrict__ core, int r_out, 
     for (int i = threadIdx.x; i < r_out * p * r_in; i += blockDim.x) csm[i] = core[i];
     __syncthreads();
     const int64_t N = in.N;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
-        double phi[PB];
-        basis_values<PB>(in, j, s, 0, phi);
-        double rb[RB];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s0 < N; s0 += stride * kSB) {
+        double phi[kSB][PB], rb[kSB][RB];
+        int64_t sidx[kSB];
 #pragma unroll
-        for (int b = 0; b < RB; b++) rb[b] = (b < r_in) ? (Rin ? Rin[(int64_t)b * N + s] : 1.0) : 0.0;
+        for (int u = 0; u < kSB; u++) {
+            const int64_t s = s0 + u * stride;
+            sidx[u] = s < N ? s : N - 1;
+#pragma unroll
+            for (int b = 0; b < RB; b++) rb[u][b] = (b < r_in) ? (Rin ? Rin[(int64_t)b * N + sidx[u]] : 1.0) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kSB; u++) basis_values<PB>(in, j, sidx[u], 0, phi[u]);
         for (int a = 0; a < r_out; a++) {
-            double acc = 0.0;
+            double acc[kSB];
+#pragma unroll
+            for (int u = 0; u < kSB; u++) acc[u] = 0.0;
 #pragma unroll
             for (int m = 0; m < PB; m++) {
                 if (m < p) {
                     const double* c = csm + (a * p + m) * r_in;
-                    double t = 0.0;
+                    double t[kSB];
+#pragma unroll
+                    for (int u = 0; u < kSB; u++) t[u] = 0.0;
 #pragma unroll
                     for (int b = 0; b < RB; b++)
-                        if (b < r_in) t = fma(c[b], rb[b], t);
-                    acc = fma(phi[m], t, acc);
+                        if (b < r_in) {
+                            const double cb = c[b];
+#pragma unroll
+                            for (int u = 0; u < kSB; u++) t[u] = fma(cb, rb[u][b], t[u]);
+                        }
+#pragma unroll
+                    for (int u = 0; u < kSB; u++) acc[u] = fma(phi[u][m], t[u], acc[u]);
                 }
             }
-            Rout[(int64_t)a * N + s] = acc;
+#pragma unroll
+            for (int u = 0; u < kSB; u++) {
+                const int64_t s = s0 + u * stride;
+                if (s < N) Rout[(int64_t)a * N + s] = acc[u];
+            }
         }
     }
 }
@@ -262,7 +323,7 @@ template <int RB>
 int pick_pb_left(int p, Inputs in, int j, const double* core, int r_in, int r_out, const double* Lin, double* Lout,
                  cudaStream_t st) {
     const size_t sm = sizeof(double) * r_in * p * r_out;
-    const int g = grid_for(in.N);
+    const int g = grid_for_blocked(in.N);
     if (p <= 4) k_interface_left<RB, 4><<<g, kThreads, sm, st>>>(in, j, core, r_in, r_out, Lin, Lout);
     else k_interface_left<RB, 8><<<g, kThreads, sm, st>>>(in, j, core, r_in, r_out, Lin, Lout);
     return 0;
@@ -271,7 +332,7 @@ template <int RB>
 int pick_pb_right(int p, Inputs in, int j, const double* core, int r_out, int r_in, const double* Rin, double* Rout,
                   cudaStream_t st) {
     const size_t sm = sizeof(double) * r_in * p * r_out;
-    const int g = grid_for(in.N);
+    const int g = grid_for_blocked(in.N);
     if (p <= 4) k_interface_right<RB, 4><<<g, kThreads, sm, st>>>(in, j, core, r_out, r_in, Rin, Rout);
     else k_interface_right<RB, 8><<<g, kThreads, sm, st>>>(in, j, core, r_out, r_in, Rin, Rout);
     return 0;
@@ -292,7 +353,7 @@ int launch_interface_left(const Inputs& in, int j, const double* core, int r_in,
                           double* Lout, cudaStream_t st) {
     if (in.p > kMaxP || r_in > kMaxR || r_out > kMaxR) return fail_msg(2, "interface_left: p=%d r=(%d,%d) exceeds limits", in.p, r_in, r_out);
 #define CALL(RBV) pick_pb_left<RBV>(in.p, in, j, core, r_in, r_out, Lin, Lout, st)
-    BSDE_DISPATCH_RB(r_out, CALL);
+    BSDE_DISPATCH_RB((r_out > r_in ? r_out : r_in), CALL);
 #undef CALL
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;

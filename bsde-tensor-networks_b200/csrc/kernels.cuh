@@ -37,6 +37,7 @@ struct AsmPlan {
     size_t smem_bytes = 0;
     uint16_t* d_tab = nullptr;                    // fragment-source table (layout depends on the variant)
     int32_t* d_gather = nullptr;                  // [n_mom] canonical moment -> slot in a partial row
+    uint16_t* d_expand = nullptr;                 // [n*n + n] entry of A (row-major) / b -> canonical moment
     std::vector<int32_t> h_gather;
 };
 
@@ -52,6 +53,7 @@ enum SolverId : int { SOLVER_LSTSQ = 0, SOLVER_LU = 1, SOLVER_QR = 2, SOLVER_SOL
 
 struct MicroSolveArgs {
     const double* moments;   // canonical moments of core j
+    const uint16_t* expand_map = nullptr;   // AsmPlan::d_expand
     int rl, p, rr, mono, nLL, nRR, nB;
     int direction;           // +1: left half-sweep (QR, push S right); -1: right half-sweep (push S^T left); 0: no QR
     int solver;
@@ -66,6 +68,7 @@ struct MicroSolveArgs {
     const double* gamma = nullptr;
     const double* theta = nullptr;
     int reg_left = 0, reg_right = 0;
+    long long* clk = nullptr;           // optional: 4 phase-cycle accumulators (expand, solve, QR, push)
     double* dbg_A;           // optional n*n + n (A | b) dump for parity tests
     int* info;               // accumulated: [0] cholesky solves, [1] jacobi-svd solves, [2] lu solves, [3] min numerical rank
     const double* A_direct = nullptr;   // explicit n x n system (then rl = n, p = rr = 1 and moments is unused)

@@ -65,7 +65,9 @@ BSDE_API int bsde_ctx_launch_count(bsde_ctx* ctx, int64_t* out);
  * CUDA events by class and disable graphs; setting it resets the counters) */
 BSDE_API int bsde_ctx_set_option(bsde_ctx* ctx, const char* name, int64_t value);
 /* stats: "<class>_ms" / "<class>_n" for class in assembly, reduce, allreduce, solve, interface (device time and
- * launch count accumulated while "profile" is on); "sm_count"; "workspace_bytes" */
+ * launch count accumulated while "profile" is on); "solve_phase0".."solve_phase3" (SM cycles spent by the solve
+ * kernel in moment expansion / solve / QR / factor push, accumulated while "profile" is on); "sm_count";
+ * "workspace_bytes" */
 BSDE_API int bsde_ctx_get_stat(bsde_ctx* ctx, const char* name, double* out);
 
 /* sample-sharded data parallelism: one process per GPU, NCCL all-reduce of the per-core moments.
