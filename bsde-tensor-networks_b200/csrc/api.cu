@@ -333,7 +333,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     const AsmPlan* P;
     BSDE_TRY(get_plan(c, rl, T.p, rr, m.mono, m.in->N, &P));
     BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
-    BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->n_mom));
+    BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride));
     cudaEvent_t e0 = prof_mark(c), e1 = prof_take(c);
     BSDE_TRY(launch_assembly(*P, *m.in, j, j == 0 ? nullptr : m.B->at(j), j == T.d - 1 ? nullptr : m.B->at(j + 1), m.y,
                              c->partial.as<double>(), c->moments.as<double>(), c->stream, e1));
@@ -341,12 +341,13 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     cudaEvent_t e2 = prof_mark(c);
     prof_span(c, bsde_ctx::P_ASSEMBLY, e0, e1);
     prof_span(c, bsde_ctx::P_REDUCE, e1, e2);
-    BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), P->n_mom));
+    BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), (int)P->partial_stride));
     cudaEvent_t e3 = c->world > 1 ? prof_mark(c) : e2;
     if (c->world > 1) prof_span(c, bsde_ctx::P_ALLREDUCE, e2, e3);
     MicroSolveArgs a{};
     a.moments = c->moments.as<double>();
     a.expand_map = P->d_expand;
+    a.n_slots = (int)P->partial_stride;
     a.rl = rl; a.p = T.p; a.rr = rr; a.mono = m.mono; a.nLL = P->nLL; a.nRR = P->nRR; a.nB = P->nB;
     a.direction = direction; a.solver = m.solver;
     a.core_j = T.core(j);

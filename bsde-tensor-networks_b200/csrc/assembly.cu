@@ -344,35 +344,39 @@ k_assemble(AsmArgs a) {
     write_partials<NJ>(a, sm, ws, acc, accyy, lane, group * NJ, group == 0);
 }
 
-// moments[e] = sum over partial rows of partial[row][gather[e]].  One block = 32 consecutive moments x 32 row
-// lanes: warp w adds rows w, w+32, ... in order, then the warp sums are added in warp order, so the result is
-// a fixed summation tree of the launch shape (bitwise reproducible).
+// sums[e] = sum over the CTAs' partial rows of partial[row][e], e = slot of a partial row (tile * 64 + r * 8 + c, last
+// slot = y.y).  Coalesced: one block = 32 consecutive slots x 32 row lanes; warp w adds rows w, w+32, ... in order
+// (14 independent loads in flight at 444 rows), then the warp sums are added in warp order — a fixed summation tree of
+// the launch shape, hence bitwise reproducible.  The solve kernel reads the sums through AsmPlan::d_expand.
 constexpr int kRedWarps = 32;
 __global__ void __launch_bounds__(32 * kRedWarps)
-k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride,
-                const int32_t* __restrict__ gather, int n_mom, double* __restrict__ moments) {
+k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, int n_slots, double* __restrict__ sums) {
     __shared__ double part[kRedWarps][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (e < n_mom) {
-        const int32_t g = gather[e];
-        int q = w;
-        for (; q + 3 * kRedWarps < rows; q += 4 * kRedWarps) {
-            a0 += partial[(int64_t)q * stride + g];
-            a1 += partial[(int64_t)(q + kRedWarps) * stride + g];
-            a2 += partial[(int64_t)(q + 2 * kRedWarps) * stride + g];
-            a3 += partial[(int64_t)(q + 3 * kRedWarps) * stride + g];
+    double acc[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) acc[u] = 0.0;
+    if (e < n_slots) {
+        for (int q0 = w; q0 < rows; q0 += 16 * kRedWarps) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int q = q0 + u * kRedWarps;
+                if (q < rows) acc[u] += partial[(int64_t)q * stride + e];
+            }
         }
-        for (; q < rows; q += kRedWarps) a0 += partial[(int64_t)q * stride + g];
     }
-    part[w][lane] = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int h = 8; h > 0; h >>= 1)
+#pragma unroll
+        for (int u = 0; u < h; u++) acc[u] += acc[u + h];
+    part[w][lane] = acc[0];
     __syncthreads();
-    if (w == 0 && e < n_mom) {
+    if (w == 0 && e < n_slots) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < kRedWarps; k++) t += part[k][lane];
-        moments[e] = t;
+        sums[e] = t;
     }
 }
 
@@ -582,11 +586,11 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
                 const int a2 = col / (p * rr), m2 = (col / rr) % p, b2 = col % rr;
                 const int lam = pair_index(a1, a2, rl), rho = pair_index(b1, b2, rr);
                 const int beta = mono ? (m1 + m2) : pair_index(m1, m2, p);
-                emap[(size_t)row * n + col] = (uint16_t)((beta * P.nLL + lam) * P.nRR + rho);
+                emap[(size_t)row * n + col] = (uint16_t)P.h_gather[(beta * P.nLL + lam) * P.nRR + rho];
             }
-            emap[(size_t)n * n + row] = (uint16_t)(base2 + (m1 * rl + a1) * rr + b1);
+            emap[(size_t)n * n + row] = (uint16_t)P.h_gather[base2 + (m1 * rl + a1) * rr + b1];
         }
-        if (P.n_mom > 65535) return fail_msg(2, "assembly: %d moments exceed the 16-bit expansion map", P.n_mom);
+        if (P.partial_stride > 65535) return fail_msg(2, "assembly: %lld partial slots exceed the 16-bit expansion map", (long long)P.partial_stride);
         BSDE_CUDA_OK(cudaMalloc(&P.d_expand, emap.size() * sizeof(uint16_t)));
         BSDE_CUDA_OK(cudaMemcpy(P.d_expand, emap.data(), emap.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
@@ -616,7 +620,7 @@ int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, 
     const int rc = dispatch(OP_LAUNCH, P, &a, st, nullptr);
     if (rc) return rc;
     if (mid) BSDE_CUDA_OK(cudaEventRecord(mid, st));
-    k_moment_reduce<<<(P.n_mom + 31) / 32, 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride, P.d_gather, P.n_mom, moments);
+    k_moment_reduce<<<(int)((P.partial_stride + 31) / 32), 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride, (int)P.partial_stride, moments);
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -90,6 +90,103 @@ __device__ void warp_householder_qr(double* M, int m, int k, int ld, double* Rm,
     }
 }
 
+// 1 / d to ~1 ulp without the IEEE division sequence (approximate reciprocal + two Newton steps): FP64 has ~75 cycles of
+// dependent-issue latency here, so the length of the dependent chain is what a one-warp factorisation costs.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
+
+// Householder QR of M (m x k row-major, ld; m <= 64, k <= KM) by one warp with the matrix held in registers: lane l owns
+// rows l and l + 32.  Same reflectors and sign convention as warp_householder_qr (LAPACK dgeqr2 / dorg2r), but every
+// column costs two batched warp reductions instead of one per trailing column, and no shared-memory round trips.
+template <int KM>
+__device__ void warp_householder_qr_regs(double* M, int m, int k, int ld, double* Rm) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool h0 = lane < m, h1 = lane + 32 < m;
+    double x0[KM], x1[KM], tau[KM];
+#pragma unroll
+    for (int c = 0; c < KM; c++) {
+        x0[c] = (h0 && c < k) ? M[lane * ld + c] : 0.0;
+        x1[c] = (h1 && c < k) ? M[(lane + 32) * ld + c] : 0.0;
+        tau[c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < KM; c++) {
+        if (c >= k) break;
+        double ss = ((lane > c) ? x0[c] * x0[c] : 0.0) + x1[c] * x1[c];
+        ss = warp_sum(ss);
+        const double alpha = __shfl_sync(full, x0[c], c);
+        double t = 0.0, beta = alpha, scale = 0.0;
+        if (ss != 0.0) {
+            const double s2 = fma(alpha, alpha, ss);
+            const double rs = rsqrt(s2);
+            beta = -copysign(s2 * rs, alpha);
+            t = fma(fabs(alpha), rs, 1.0);                   // (beta - alpha) / beta
+            scale = fast_rcp(alpha - beta);
+        }
+        tau[c] = t;
+        if (lane > c) x0[c] *= scale;
+        x1[c] *= scale;
+        if (lane == c) x0[c] = beta;
+        const double v0 = (lane > c) ? x0[c] : (lane == c ? 1.0 : 0.0), v1 = x1[c];
+        double w[KM];
+#pragma unroll
+        for (int cc = 0; cc < KM; cc++) w[cc] = (cc > c && cc < k) ? fma(v0, x0[cc], v1 * x1[cc]) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int cc = 0; cc < KM; cc++)
+                if (cc > c) w[cc] += __shfl_xor_sync(full, w[cc], o);
+#pragma unroll
+        for (int cc = 0; cc < KM; cc++)
+            if (cc > c && cc < k) {
+                const double tw = t * w[cc];
+                x0[cc] = fma(-tw, v0, x0[cc]);
+                x1[cc] = fma(-tw, v1, x1[cc]);
+            }
+    }
+    // R: row c lives in lane c
+#pragma unroll
+    for (int c = 0; c < KM; c++)
+        if (c < k && lane < k) Rm[lane * k + c] = (c >= lane) ? x0[c] : 0.0;
+    // Q = H_0 ... H_{k-1} [I_k; 0]
+    double q0[KM], q1[KM];
+#pragma unroll
+    for (int c = 0; c < KM; c++) { q0[c] = (lane == c && c < k) ? 1.0 : 0.0; q1[c] = 0.0; }
+#pragma unroll
+    for (int c = KM - 1; c >= 0; c--) {
+        if (c >= k) continue;
+        const double v0 = (lane > c) ? x0[c] : (lane == c ? 1.0 : 0.0), v1 = x1[c];
+        double w[KM];
+#pragma unroll
+        for (int cc = 0; cc < KM; cc++) w[cc] = (cc >= c && cc < k) ? fma(v0, q0[cc], v1 * q1[cc]) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int cc = 0; cc < KM; cc++)
+                if (cc >= c) w[cc] += __shfl_xor_sync(full, w[cc], o);
+#pragma unroll
+        for (int cc = 0; cc < KM; cc++)
+            if (cc >= c && cc < k) {
+                const double tw = tau[c] * w[cc];
+                q0[cc] = fma(-tw, v0, q0[cc]);
+                q1[cc] = fma(-tw, v1, q1[cc]);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < KM; c++)
+        if (c < k) {
+            if (h0) M[lane * ld + c] = q0[c];
+            if (h1) M[(lane + 32) * ld + c] = q1[c];
+        }
+    __syncwarp();
+}
+
 struct SolveScratch {
     double* A;      // (n+1) x (n+1) augmented, row-major, ld = n+1
     double* G;      // n x n column-major (Jacobi)        — aliases A
@@ -108,9 +205,9 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
         return;
     }
     // stage the moments in shared memory with coalesced loads (the gather below would otherwise pay one L2 round trip
-    // per entry); `stage` is the V / scratch area that is free until the solve starts
-    const int n_m1 = a.nB * a.nLL * a.nRR, n_mom = n_m1 + n;
-    for (int e = threadIdx.x; e < n_mom; e += blockDim.x) stage[e] = a.moments[e];
+    // per entry)
+    // (a.moments holds the summed partial-row slots of the assembly kernel; a.n_slots of them)
+    for (int e = threadIdx.x; e < a.n_slots; e += blockDim.x) stage[e] = a.moments[e];
     __syncthreads();
     // a.expand_map[e] (built once per core shape on the host, assembly.cu) = index of the moment that entry e of the
     // row-major A (then of b) is equal to: A[(a,m,b),(a',m',b')] = M1[beta(m,m')][lambda(a,a')][rho(b,b')]
@@ -429,10 +526,11 @@ k_micro_solve(MicroSolveArgs a) {
     double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
     double* tau = qrR + kMaxR * kMaxR;          // kMaxR
     double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
+    double* stage_buf = vbuf + kMaxR * kMaxP + 16;   // a.n_slots : the assembly kernel's summed slots
     __shared__ int s_path, s_rank, s_ok;
     __shared__ double s_red[4];
 
-    expand_normal_equations(a, S.A, ld, S.bvec, S.V);
+    expand_normal_equations(a, S.A, ld, S.bvec, stage_buf);
     __syncthreads();
     BSDE_PHASE(0);
     if (a.dbg_A) {
@@ -448,7 +546,7 @@ k_micro_solve(MicroSolveArgs a) {
         __syncthreads();
         if (!s_ok) {
             // rebuild A (column-major == row-major, A is symmetric) with ld = n for the Jacobi path
-            expand_normal_equations(a, S.G, n, S.bvec, S.V);
+            expand_normal_equations(a, S.G, n, S.bvec, stage_buf);
             __syncthreads();
             double* xtmp = S.red;
             const int rank = jacobi_lstsq(S, n, S.bvec, xtmp);
@@ -477,7 +575,11 @@ k_micro_solve(MicroSolveArgs a) {
         const int mrows = a.rl * a.p, k = a.rr;            // left_unfold(X): (rl*p) x rr, row-major == x itself
         for (int i = threadIdx.x; i < n; i += blockDim.x) Mq[i] = S.x[i];
         __syncthreads();
-        if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
+        if (threadIdx.x < 32) {
+            if (mrows <= 64 && k <= 4) warp_householder_qr_regs<4>(Mq, mrows, k, k, qrR);
+            else if (mrows <= 64 && k <= 8) warp_householder_qr_regs<8>(Mq, mrows, k, k, qrR);
+            else warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
+        }
         __syncthreads();
         BSDE_PHASE(2);
         for (int i = threadIdx.x; i < n; i += blockDim.x) a.core_j[i] = Mq[i];
@@ -498,7 +600,11 @@ k_micro_solve(MicroSolveArgs a) {
             Mq[e] = S.x[c * mrows + r];
         }
         __syncthreads();
-        if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
+        if (threadIdx.x < 32) {
+            if (mrows <= 64 && k <= 4) warp_householder_qr_regs<4>(Mq, mrows, k, k, qrR);
+            else if (mrows <= 64 && k <= 8) warp_householder_qr_regs<8>(Mq, mrows, k, k, qrR);
+            else warp_householder_qr(Mq, mrows, k, k, qrR, tau, vbuf);
+        }
         __syncthreads();
         BSDE_PHASE(2);
         for (int e = threadIdx.x; e < n; e += blockDim.x) {   // core_j = Q^T
@@ -592,7 +698,7 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st) {
     if (a.direction < 0 && a.p * a.rr < a.rl) return fail_msg(2, "micro_solve: right QR needs p*r_{j+1} >= r_j (%d*%d < %d)", a.p, a.rr, a.rl);
     // keep in sync with the layout at the top of k_micro_solve
     const size_t doubles = (size_t)(n + 2) * (n + 1) + (size_t)n * n + 4 * (size_t)n + kMaxR * kMaxP * kMaxR +
-                           kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16;
+                           kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16 + (size_t)(a.n_slots > 0 ? a.n_slots : 0) + 16;
     const size_t bytes = doubles * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {

@@ -37,7 +37,7 @@ struct AsmPlan {
     size_t smem_bytes = 0;
     uint16_t* d_tab = nullptr;                    // fragment-source table (layout depends on the variant)
     int32_t* d_gather = nullptr;                  // [n_mom] canonical moment -> slot in a partial row
-    uint16_t* d_expand = nullptr;                 // [n*n + n] entry of A (row-major) / b -> canonical moment
+    uint16_t* d_expand = nullptr;                 // [n*n + n] entry of A (row-major) / b -> slot of a partial row
     std::vector<int32_t> h_gather;
 };
 
@@ -52,7 +52,8 @@ int launch_assembly(const AsmPlan& plan, const Inputs& in, int j, const double* 
 enum SolverId : int { SOLVER_LSTSQ = 0, SOLVER_LU = 1, SOLVER_QR = 2, SOLVER_SOLVE = 3 };
 
 struct MicroSolveArgs {
-    const double* moments;   // canonical moments of core j
+    const double* moments;   // summed partial-row slots of the assembly kernel (AsmPlan::partial_stride of them)
+    int n_slots = 0;
     const uint16_t* expand_map = nullptr;   // AsmPlan::d_expand
     int rl, p, rr, mono, nLL, nRR, nB;
     int direction;           // +1: left half-sweep (QR, push S right); -1: right half-sweep (push S^T left); 0: no QR
