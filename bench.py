@@ -318,6 +318,7 @@ def main():
             "config": workload_config(world) if N == N_PER_GPU else dict(workload_config(world), samples_per_gpu=N, workload="reduced-N debugging run (not the benchmark)"),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "fit_relative_residual": fit_quality, "solves_per_fit": solve_paths,
+            "allreduce": (None if world == 1 else ("fused into the reduction kernel over NVLink peer memory" if getattr(be, "p2p", False) else "ncclAllReduce")),
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -110,6 +110,12 @@ struct bsde_ctx {
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
     bool capturing = false;
+    // fused NVLink all-reduce (bsde_comm_p2p_*): buffers of this rank and the peers' mappings
+    PeerExchange px;
+    bool px_on = false;
+    double* px_data_local = nullptr;
+    unsigned long long* px_flags_local = nullptr;
+    void* px_opened[2 * kXMaxWorld] = {};
 };
 
 namespace {
@@ -336,14 +342,17 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride));
     cudaEvent_t e0 = prof_mark(c), e1 = prof_take(c);
     BSDE_TRY(launch_assembly(*P, *m.in, j, j == 0 ? nullptr : m.B->at(j), j == T.d - 1 ? nullptr : m.B->at(j + 1), m.y,
-                             c->partial.as<double>(), c->moments.as<double>(), c->stream, e1));
+                             c->partial.as<double>(), c->moments.as<double>(), c->stream, e1, c->px_on ? &c->px : nullptr));
     c->launches += 2;
     cudaEvent_t e2 = prof_mark(c);
     prof_span(c, bsde_ctx::P_ASSEMBLY, e0, e1);
     prof_span(c, bsde_ctx::P_REDUCE, e1, e2);
-    BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), (int)P->partial_stride));
-    cudaEvent_t e3 = c->world > 1 ? prof_mark(c) : e2;
-    if (c->world > 1) prof_span(c, bsde_ctx::P_ALLREDUCE, e2, e3);
+    cudaEvent_t e3 = e2;
+    if (c->world > 1 && !c->px_on) {          // NCCL path; with the peer exchange the all-reduce is inside the reduce kernel
+        BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), (int)P->partial_stride));
+        e3 = prof_mark(c);
+        prof_span(c, bsde_ctx::P_ALLREDUCE, e2, e3);
+    }
     MicroSolveArgs a{};
     a.moments = c->moments.as<double>();
     a.expand_map = P->d_expand;
@@ -386,6 +395,14 @@ int als_sweep(bsde_ctx* c, const MicroCtx& m) {
         c->launches++;
         prof_span(c, bsde_ctx::P_INTERFACE, e0, prof_mark(c));
     }
+    return 0;
+}
+
+int px_check(bsde_ctx* c) {       // after a synchronised fit: did a peer wait time out?
+    if (!c->px_on) return 0;
+    int err = 0;
+    BSDE_CUDA_OK(cudaMemcpy(&err, c->px.error, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail_msg(3, "peer all-reduce timed out waiting for another rank (rank %d of %d)", c->rank, c->world);
     return 0;
 }
 
@@ -454,6 +471,7 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
         }
     }
     BSDE_TRY(train_download(c, T, cores_host));
+    BSDE_TRY(px_check(c));
     prof_collect(c);
     if (info_host) {
         BSDE_CUDA_OK(cudaMemcpy(info_host, info, sizeof(int) * 4, cudaMemcpyDeviceToHost));
@@ -590,6 +608,7 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
         }
     }
     BSDE_TRY(train_download(c, T, cores_host));
+    BSDE_TRY(px_check(c));
     for (int k = 0; k <= d; k++) ranks[k] = T.ranks[k];
     if (state_out_host) {
         BSDE_CUDA_OK(cudaMemcpy(state_out_host, state, sizeof(double) * 3, cudaMemcpyDeviceToHost));
@@ -637,6 +656,9 @@ int bsde_ctx_destroy(bsde_ctx* c) {
     for (auto& kv : c->plans) asm_plan_free(kv.second);
     for (DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg})
         b->release();
+    for (void* q : c->px_opened) if (q) cudaIpcCloseMemHandle(q);
+    if (c->px_data_local) cudaFree(c->px_data_local);
+    if (c->px_flags_local) cudaFree(c->px_flags_local);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->own);
     delete c;
@@ -730,6 +752,50 @@ int bsde_comm_init(bsde_ctx* c, const void* id128, int rank, int world) {
     const int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
     if (rc) return fail_msg(3, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(rc));
     c->rank = rank; c->world = world;
+    return 0;
+}
+
+int bsde_comm_p2p_export(bsde_ctx* c, void* out128) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (!out128) return fail_msg(2, "bsde_comm_p2p_export: out is null");
+    if (c->world < 2 || c->world > kXMaxWorld) return fail_msg(2, "bsde_comm_p2p_export: call bsde_comm_init first (world 2..%d)", kXMaxWorld);
+    if (!c->px_data_local) {
+        const size_t nd = (size_t)2 * kXMaxWorld * kXSlots * sizeof(double);
+        const size_t nf = (size_t)2 * kXMaxWorld * kXBlocks * sizeof(unsigned long long) + kXBlocks * sizeof(unsigned long long) + 64;
+        BSDE_CUDA_OK(cudaMalloc(&c->px_data_local, nd));
+        BSDE_CUDA_OK(cudaMalloc(&c->px_flags_local, nf));
+        BSDE_CUDA_OK(cudaMemset(c->px_data_local, 0, nd));
+        BSDE_CUDA_OK(cudaMemset(c->px_flags_local, 0, nf));
+    }
+    cudaIpcMemHandle_t h[2];
+    BSDE_CUDA_OK(cudaIpcGetMemHandle(&h[0], c->px_data_local));
+    BSDE_CUDA_OK(cudaIpcGetMemHandle(&h[1], c->px_flags_local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(out128, h, 128);
+    return 0;
+}
+
+int bsde_comm_p2p_open(bsde_ctx* c, const void* all_handles, int enable) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (!enable) { c->px_on = false; return 0; }
+    if (!all_handles || !c->px_data_local) return fail_msg(2, "bsde_comm_p2p_open: export first");
+    const int W = c->world;
+    c->px.world = W; c->px.rank = c->rank;
+    for (int p = 0; p < W; p++) {
+        if (p == c->rank) { c->px.data[p] = c->px_data_local; c->px.flags[p] = c->px_flags_local; continue; }
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, (const char*)all_handles + (size_t)p * 128, 128);
+        void *pd = nullptr, *pf = nullptr;
+        BSDE_CUDA_OK(cudaIpcOpenMemHandle(&pd, h[0], cudaIpcMemLazyEnablePeerAccess));
+        BSDE_CUDA_OK(cudaIpcOpenMemHandle(&pf, h[1], cudaIpcMemLazyEnablePeerAccess));
+        c->px_opened[2 * p] = pd; c->px_opened[2 * p + 1] = pf;
+        c->px.data[p] = (double*)pd; c->px.flags[p] = (unsigned long long*)pf;
+    }
+    c->px.step = c->px_flags_local + (size_t)2 * kXMaxWorld * kXBlocks;
+    c->px.error = (int*)(c->px.step + kXBlocks);
+    c->px_on = true;
     return 0;
 }
 

@@ -350,7 +350,8 @@ k_assemble(AsmArgs a) {
 // the launch shape, hence bitwise reproducible.  The solve kernel reads the sums through AsmPlan::d_expand.
 constexpr int kRedWarps = 32;
 __global__ void __launch_bounds__(32 * kRedWarps)
-k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, int n_slots, double* __restrict__ sums) {
+k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, int n_slots, double* __restrict__ sums,
+                PeerExchange px) {
     __shared__ double part[kRedWarps][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
@@ -372,12 +373,38 @@ k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, in
         for (int u = 0; u < h; u++) acc[u] += acc[u + h];
     part[w][lane] = acc[0];
     __syncthreads();
-    if (w == 0 && e < n_slots) {
-        double t = 0.0;
+    if (w != 0) return;
+    double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < kRedWarps; k++) t += part[k][lane];
-        sums[e] = t;
+    for (int k = 0; k < kRedWarps; k++) t += part[k][lane];
+    if (px.world > 1) {
+        // ---- fused all-reduce over NVLink peer memory: push this block's 32 sums into every rank's buffer, publish a
+        // flag per (source rank, block), wait for the same block of every other rank, add in rank order.  Every rank
+        // adds the same numbers in the same order, so all replicas end with bit-identical sums.  Buffers alternate
+        // with the parity of the launch count: a rank can only be one exchange ahead of the slowest one.
+        const unsigned long long seq = px.step[blockIdx.x] + 1;
+        const size_t par = (size_t)(seq & 1ull) * px.world;
+        const int slot = blockIdx.x * 32 + lane;
+        for (int p = 0; p < px.world; p++) px.data[p][(par + px.rank) * kXSlots + slot] = t;
+        __threadfence_system();
+        __syncwarp();
+        if (lane < px.world)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[lane] + (par + px.rank) * kXBlocks + blockIdx.x), "l"(seq) : "memory");
+        if (lane < px.world) {
+            const unsigned long long* f = px.flags[px.rank] + (par + lane) * kXBlocks + blockIdx.x;
+            const long long t0 = clock64();
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v < seq && clock64() - t0 > 4000000000ll) { *px.error = 1; break; }     // ~2 s: a peer is gone
+            } while (v < seq);
+        }
+        __syncwarp();
+        t = 0.0;
+        for (int q = 0; q < px.world; q++) t += __ldcg(px.data[px.rank] + (par + q) * kXSlots + slot);
+        if (lane == 0) px.step[blockIdx.x] = seq;
     }
+    if (e < n_slots) sums[e] = t;
 }
 
 // ---- dispatch ----------------------------------------------------------------------------------------
@@ -609,7 +636,7 @@ void asm_plan_free(AsmPlan& P) {
 }
 
 int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, const double* R, const double* y,
-                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid) {
+                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid, const PeerExchange* px) {
     AsmArgs a;
     a.in = in; a.j = j; a.L = L; a.R = R; a.y = y;
     a.rl = P.rl; a.rr = P.rr; a.mono = P.mono; a.nB = P.nB;
@@ -620,7 +647,13 @@ int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, 
     const int rc = dispatch(OP_LAUNCH, P, &a, st, nullptr);
     if (rc) return rc;
     if (mid) BSDE_CUDA_OK(cudaEventRecord(mid, st));
-    k_moment_reduce<<<(int)((P.partial_stride + 31) / 32), 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride, (int)P.partial_stride, moments);
+    const int red_blocks = (int)((P.partial_stride + 31) / 32);
+    PeerExchange ex;
+    if (px && px->world > 1) {
+        if (red_blocks > kXBlocks || red_blocks * 32 > kXSlots) return fail_msg(2, "assembly: %d reduce blocks exceed the peer-exchange buffer", red_blocks);
+        ex = *px;
+    }
+    k_moment_reduce<<<red_blocks, 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride, (int)P.partial_stride, moments, ex);
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -386,6 +386,9 @@ __device__ int jacobi_lstsq(SolveScratch& S, int n, const double* bvec, double* 
         __syncthreads();
         // columns whose norm is far below the truncation cutoff (eps*n*s_max) carry only rounding noise: rotating them
         // never converges in a relative sense and they are dropped from the solution anyway
+        // (threshold = 1e-2 of the truncation cutoff in norm: a column that small at the start of a sweep cannot carry a
+        // singular direction that survives the truncation; 0.5 of the cutoff was tried and is NOT safe — unconverged
+        // columns below it still mix directions above it, which moved the C1 pipeline's Y0 by 2e-6)
         const double negligible = 1e-4 * (DBL_EPSILON * n) * (DBL_EPSILON * n) * s_nmax;
         for (int step = 0; step < m - 1; step++) {
             for (int k = warp; k < m / 2; k += nwarps) {
@@ -426,6 +429,9 @@ __device__ int jacobi_lstsq(SolveScratch& S, int n, const double* bvec, double* 
         }
         const int rot = s_rot;
         __syncthreads();
+#ifdef BSDE_DEBUG_JACOBI
+        if (threadIdx.x == 0 && (!rot || sweep == 39)) printf("jacobi n=%d sweeps=%d\n", n, sweep + 1);
+#endif
         if (!rot) break;
     }
     // singular values, projections u_i . b

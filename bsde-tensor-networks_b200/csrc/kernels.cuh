@@ -41,12 +41,26 @@ struct AsmPlan {
     std::vector<int32_t> h_gather;
 };
 
+// One-shot all-reduce of the assembly sums over NVLink peer memory, fused into k_moment_reduce (assembly.cu).
+// Every rank owns an exchange buffer that all ranks of the node map through CUDA IPC.
+constexpr int kXSlots = 4096;     // doubles per (parity, source rank)
+constexpr int kXBlocks = 160;     // reduce-kernel blocks (32 slots each) that can take part
+constexpr int kXMaxWorld = 8;
+struct PeerExchange {
+    int world = 1, rank = 0;
+    double* data[kXMaxWorld] = {};                 // data[p]  : rank p's buffer  [2][world][kXSlots]
+    unsigned long long* flags[kXMaxWorld] = {};    // flags[p] : rank p's flags   [2][world][kXBlocks]
+    unsigned long long* step = nullptr;            // local    : [kXBlocks] launches seen by each block
+    int* error = nullptr;                          // local    : set to 1 when a wait timed out
+};
+
 int asm_plan_build(AsmPlan& plan, int rl, int p, int rr, int mono, int64_t N, int sm_count, int force_generic = 0);
 void asm_plan_free(AsmPlan& plan);
 // Launches the assembly kernel and the partial reduction; `moments` (n_mom doubles, device) receives
 // [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y].
 int launch_assembly(const AsmPlan& plan, const Inputs& in, int j, const double* L, const double* R, const double* y,
-                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid = nullptr);
+                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid = nullptr,
+                    const PeerExchange* px = nullptr);
 
 // ---- dense.cu ------------------------------------------------------------------------------------
 enum SolverId : int { SOLVER_LSTSQ = 0, SOLVER_LU = 1, SOLVER_QR = 2, SOLVER_SOLVE = 3 };

@@ -136,6 +136,27 @@ class Backend:
         uid = t.cpu().numpy().copy()
         check(self.lib.bsde_comm_init(self.ctx, uid.ctypes.data_as(C.c_void_p), rank, world))
         self.rank, self.world = rank, world
+        # fused all-reduce over NVLink peer memory (one node, <= 8 ranks); every rank must take the same decision
+        self.p2p = False
+        want = os.environ.get("BSDE_P2P", "1") != "0" and world <= 8 and dist.get_backend() == "nccl"
+        mine = np.zeros(128, dtype=np.uint8)
+        ok = 0
+        if want:
+            ok = 1 if self.lib.bsde_comm_p2p_export(self.ctx, mine.ctypes.data_as(C.c_void_p)) == 0 else 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.tdev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            handles = [torch.empty(128, dtype=torch.uint8, device=self.tdev) for _ in range(world)]
+            dist.all_gather(handles, torch.from_numpy(mine).to(self.tdev))
+            allh = np.concatenate([h.cpu().numpy() for h in handles])
+            ok = 1 if self.lib.bsde_comm_p2p_open(self.ctx, allh.ctypes.data_as(C.c_void_p), 1) == 0 else 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.tdev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                self.p2p = True
+            else:
+                check(self.lib.bsde_comm_p2p_open(self.ctx, None, 0))
+        dist.barrier()
 
     # ---- the hot path ------------------------------------------------------------------------------------
     def fit_als(self, inp: DeviceInputs, y, n_iter, ranks, solver_id, cores_flat):

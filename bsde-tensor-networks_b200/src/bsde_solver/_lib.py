@@ -33,6 +33,8 @@ SIGNATURES = {
     "bsde_ctx_get_stat": [_vp, C.c_char_p, C.POINTER(C.c_double)],
     "bsde_comm_unique_id": [_vp],
     "bsde_comm_init": [_vp, _vp, C.c_int, C.c_int],
+    "bsde_comm_p2p_export": [_vp, _vp],
+    "bsde_comm_p2p_open": [_vp, _vp, C.c_int],
     "bsde_malloc": [_vp, _i64, C.POINTER(_vp)],
     "bsde_free": [_vp, _vp],
     "bsde_memcpy_h2d": [_vp, _vp, _vp, _i64],

@@ -75,6 +75,13 @@ BSDE_API int bsde_ctx_get_stat(bsde_ctx* ctx, const char* name, double* out);
 BSDE_API int bsde_comm_unique_id(void* out128);
 BSDE_API int bsde_comm_init(bsde_ctx* ctx, const void* id128, int rank, int world);
 
+/* Optional, after bsde_comm_init on a single NVLink node (world <= 8): fuse the all-reduce of the per-core moments into
+ * the reduction kernel over peer memory instead of calling NCCL.  bsde_comm_p2p_export fills 128 bytes (two CUDA IPC
+ * handles) per rank; gather them from all ranks in rank order (world x 128 bytes) and call bsde_comm_p2p_open with
+ * enable = 1 on every rank (all ranks must take the same decision; enable = 0 keeps NCCL). */
+BSDE_API int bsde_comm_p2p_export(bsde_ctx* ctx, void* out128);
+BSDE_API int bsde_comm_p2p_open(bsde_ctx* ctx, const void* all_handles, int enable);
+
 /* plain device memory helpers so a C caller needs nothing but this library */
 BSDE_API int bsde_malloc(bsde_ctx* ctx, int64_t bytes, void** out_dev);
 BSDE_API int bsde_free(bsde_ctx* ctx, void* ptr_dev);

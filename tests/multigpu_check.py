@@ -56,7 +56,8 @@ def main():
         fit = be.tt_eval(DeviceInputs(BASIS_POLY, p, xT), ranks, cores)
         err = float(torch.linalg.vector_norm(fit - fit_full) / torch.linalg.vector_norm(fit_full))
         if rank == 0:
-            print(f"world {world} use_graph {use_graph}: replicas bit-identical {identical}, fitted values vs single GPU {err:.2e}")
+            print(f"world {world} use_graph {use_graph} fused peer all-reduce {getattr(be, 'p2p', False)}: replicas bit-identical {identical}, "
+                  f"fitted values vs single GPU {err:.2e}")
         assert identical and err < 1e-10
     dist.destroy_process_group()
 
