@@ -235,7 +235,6 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
 }
 
 // Named barrier for the first `count` threads of the CTA (the fast path runs on 8 of the 32 warps).
-__device__ __forceinline__ void bar_sub(int) { __syncthreads(); }
 
 constexpr int kCholThreads = 1024;  // the factorisation uses the whole CTA: <= 4 trailing entries per thread and column
 constexpr double kGateSafety = 100.0;
@@ -248,7 +247,7 @@ constexpr double kGateSafety = 100.0;
 // value, i.e. that the exact solve IS the lstsq answer.  Anything else (non-positive pivot, failed test) returns
 // false and the caller takes the SVD path, which reproduces the truncation rule literally.
 __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_red) {
-    const int ld = n + 1;
+    const int ld = n + 3;                                     // odd pitch; columns n, n+1 of the upper part are used below
     double* A = S.A;
     const int tid = threadIdx.x;
     // s_red: [0] trace, [1] bad flag, [2] |z|^2
@@ -264,10 +263,10 @@ __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_r
         bad = __any_sync(0xffffffffu, bad);
         if (tid == 0) { s_red[0] = tr; s_red[1] = bad ? 1.0 : 0.0; }
     }
-    bar_sub(kCholThreads);
+    __syncthreads();
     if (s_red[1] != 0.0) return false;
-    for (int i = tid; i < n; i += kCholThreads) S.sc[i] = 1.0 / sqrt(A[i * ld + i]);
-    bar_sub(kCholThreads);
+    for (int i = tid; i < n; i += kCholThreads) S.sc[i] = rsqrt(A[i * ld + i]);
+    __syncthreads();
     // scale the lower triangle; rows n, n+1 = equilibrated right-hand sides
     for (int e = tid; e < (n + 2) * n; e += kCholThreads) {
         const int i = e / n, j = e - i * n;
@@ -275,27 +274,32 @@ __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_r
         else if (i == n + 1) A[i * ld + j] = ((((unsigned)j * 2654435761u) >> 7) & 1u ? 1.0 : -1.0) * S.sc[j];
         else if (j <= i) A[i * ld + j] *= S.sc[i] * S.sc[j];
     }
-    bar_sub(kCholThreads);
-    // Right-looking factorisation, two columns per trailing update (rank-2) and the column scaling folded into the
-    // update and the back substitution (stored column k = L_ik / dinv_k).  FP64 has ~75 cycles of dependent-issue
-    // latency on this part (bench/micro/chol64.cu), so the cost is the number of dependent FP64 operations and block
-    // barriers per pivot: every thread recomputes the 2x2 pivot block redundantly instead of waiting for a broadcast.
+    __syncthreads();
+    // Right-looking factorisation, two columns per trailing update (rank-2), ONE block barrier per column pair.
+    // FP64 has ~75 cycles of dependent-issue latency on this part (bench/micro/chol64.cu), so the cost is the number of
+    // dependent FP64 operations and barriers per pivot:
+    //   * every thread recomputes the 2x2 pivot block redundantly instead of waiting for a broadcast;
+    //   * reciprocal pivots come from rcp.approx + 2 Newton steps (5 dependent operations instead of rsqrt + square);
+    //     1/sqrt(pivot), needed only by the back substitution, is computed off the critical path;
+    //   * columns are left unscaled (stored column k = L_ik * sqrt(pivot_k)); the updated second column of a pair is
+    //     parked in the unused upper triangle (A[k+1][i]) so that no second barrier is needed to publish it.
     const int ty = tid >> 5, tx = tid & 31;
     double* dinv = S.red;                                     // 1 / sqrt(pivot_k)
     int k = 0;
     for (; k + 1 < n; k += 2) {
         const double p0 = A[k * ld + k];
         if (!(p0 > 0.0)) return false;                        // uniform: every thread reads the same values
-        const double r0 = rsqrt(p0), i0 = r0 * r0;
+        const double i0 = fast_rcp(p0);
         const double a10 = A[(k + 1) * ld + k];
         const double p1 = fma(-a10 * i0, a10, A[(k + 1) * ld + k + 1]);
         if (!(p1 > 0.0)) return false;
-        const double r1 = rsqrt(p1), i1 = r1 * r1;
-        if (tid == 0) { dinv[k] = r0; dinv[k + 1] = r1; }
+        const double i1 = fast_rcp(p1);
         for (int i = k + 2 + ty; i <= n + 1; i += 32) {
             const double ui = A[i * ld + k];
-            const double vi = fma(-ui * i0, a10, A[i * ld + k + 1]);
-            const double li0 = ui * i0, li1 = vi * i1;
+            const double li0 = ui * i0;
+            const double vi = fma(-li0, a10, A[i * ld + k + 1]);
+            const double li1 = vi * i1;
+            if (tx == 0) A[(k + 1) * ld + i] = vi;            // final column k+1, row i -> upper triangle
             const int jmax = (i < n) ? i : n - 1;
             for (int j = k + 2 + tx; j <= jmax; j += 32) {
                 const double uj = A[j * ld + k];
@@ -303,38 +307,42 @@ __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_r
                 A[i * ld + j] = fma(-li1, vj, fma(-li0, uj, A[i * ld + j]));
             }
         }
-        bar_sub(kCholThreads);
-        // column k+1 of the panel in its updated (unscaled) form, needed by the back substitution
-        for (int i = k + 2 + tid; i <= n + 1; i += kCholThreads) A[i * ld + k + 1] = fma(-A[i * ld + k] * i0, a10, A[i * ld + k + 1]);
-        if (tid == 0) A[(k + 1) * ld + k + 1] = p1;
-        bar_sub(kCholThreads);
+        if (tid == 0) { dinv[k] = rsqrt(p0); dinv[k + 1] = rsqrt(p1); }
+        __syncthreads();
     }
-    if (k < n) {                                              // odd n: last column on its own
+    if (k < n) {                                              // odd n: last column on its own (stays in the lower part)
         const double piv = A[k * ld + k];
         if (!(piv > 0.0)) return false;
-        const double r = rsqrt(piv), ipiv = r * r;
-        if (tid == 0) dinv[k] = r;
+        const double ipiv = fast_rcp(piv);
+        if (tid == 0) dinv[k] = rsqrt(piv);
         for (int i = k + 1 + ty; i <= n + 1; i += 32) {
             const double lik = A[i * ld + k] * ipiv;
             const int jmax = (i < n) ? i : n - 1;
             for (int j = k + 1 + tx; j <= jmax; j += 32) A[i * ld + j] = fma(-lik, A[j * ld + k], A[i * ld + j]);
         }
-        bar_sub(kCholThreads);
+        __syncthreads();
     }
+    const int npair = n & ~1;                                 // columns below npair with odd index live in the upper part
     // back substitution L^T x = z for both right-hand sides: warp 0 -> b, warp 1 -> probe.
-    // Stored column k holds L_ik * sqrt(pivot_k) (unscaled), rows n / n+1 hold z_k * sqrt(pivot_k).
+    // Stored column k holds L_ik * sqrt(pivot_k) (unscaled), the right-hand-side rows hold z_k * sqrt(pivot_k).
     if (tid < 64) {
         const int lane = tid & 31;
-        double* z = A + (n + (tid >> 5)) * ld;
-        for (int i = lane; i < n; i += 32) z[i] *= dinv[i];                   // z_k
+        const int zr = n + (tid >> 5);
+        double* z = A + zr * ld;
+        for (int i = lane; i < n; i += 32) {
+            const double raw = ((i & 1) && i < npair) ? A[i * ld + zr] : z[i];
+            z[i] = raw * dinv[i];                                              // z_k
+        }
         __syncwarp();
-        for (int k = n - 1; k >= 0; k--) {
-            const double dk = dinv[k];
-            const double xk = z[k] * dk;                                        // x_k = z_k / L_kk
+        for (int kk = n - 1; kk >= 0; kk--) {
+            const double xk = z[kk] * dinv[kk];                                  // x_k = z_k / L_kk
             __syncwarp();
-            if (lane == 0) z[k] = xk;
-            // L_ki = A[k][i] * dinv_i  (row k, i < k)
-            for (int i = lane; i < k; i += 32) z[i] = fma(-A[k * ld + i] * dinv[i], xk, z[i]);
+            if (lane == 0) z[kk] = xk;
+            // L_ki = (stored column i at row k) * dinv_i, i < k
+            for (int i = lane; i < kk; i += 32) {
+                const double lki = ((i & 1) && i < npair) ? A[i * ld + kk] : A[kk * ld + i];
+                z[i] = fma(-lki * dinv[i], xk, z[i]);
+            }
             __syncwarp();
         }
         if (tid < 32) {
@@ -346,7 +354,7 @@ __device__ bool cholesky_solve(SolveScratch& S, int n, double* xout, double* s_r
             if (lane == 0) s_red[2] = zz;
         }
     }
-    bar_sub(kCholThreads);
+    __syncthreads();
     const double zz = s_red[2];
     if (!isfinite(zz) || !(zz > 0.0)) return false;
     const double sigma_min_bound = sqrt((double)n / zz);
@@ -465,9 +473,9 @@ __device__ int jacobi_lstsq(SolveScratch& S, int n, const double* bvec, double* 
     return rank;
 }
 
-// Gaussian elimination with partial pivoting on [A | b] (row-major, ld = n+1, b in column n).
+// Gaussian elimination with partial pivoting on [A | b] (row-major, ld = n+3 as everywhere in the kernel, b in column n).
 __device__ void lu_solve(SolveScratch& S, int n, double* xout) {
-    const int ld = n + 1;
+    const int ld = n + 3;
     double* A = S.A;
     __shared__ int s_piv;
     for (int i = threadIdx.x; i < n; i += blockDim.x) A[i * ld + n] = S.bvec[i];
@@ -519,11 +527,11 @@ k_micro_solve(MicroSolveArgs a) {
     extern __shared__ double sm[];
     long long t_phase = a.clk ? clock64() : 0;
     const int n = a.rl * a.p * a.rr;
-    const int ld = n + 1;
+    const int ld = n + 3;
     SolveScratch S;
-    S.A = sm;                                   // (n+2) x (n+1): augmented normal equations / Jacobi G / QR work matrix
+    S.A = sm;                                   // (n+2) x (n+3): augmented normal equations / Jacobi G / QR work matrix
     S.G = sm;
-    S.V = sm + (size_t)(n + 2) * (n + 1);       // n^2     : Jacobi right vectors
+    S.V = sm + (size_t)(n + 2) * (n + 3);       // n^2     : Jacobi right vectors
     S.x = S.V + (size_t)n * n;                  // n
     S.sc = S.x + n;                             // n
     S.bvec = S.sc + n;                          // n
@@ -703,7 +711,7 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st) {
     if (a.direction > 0 && a.rl * a.p < a.rr) return fail_msg(2, "micro_solve: left QR needs r_j*p >= r_{j+1} (%d*%d < %d)", a.rl, a.p, a.rr);
     if (a.direction < 0 && a.p * a.rr < a.rl) return fail_msg(2, "micro_solve: right QR needs p*r_{j+1} >= r_j (%d*%d < %d)", a.p, a.rr, a.rl);
     // keep in sync with the layout at the top of k_micro_solve
-    const size_t doubles = (size_t)(n + 2) * (n + 1) + (size_t)n * n + 4 * (size_t)n + kMaxR * kMaxP * kMaxR +
+    const size_t doubles = (size_t)(n + 2) * (n + 3) + (size_t)n * n + 4 * (size_t)n + kMaxR * kMaxP * kMaxR +
                            kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16 + (size_t)(a.n_slots > 0 ? a.n_slots : 0) + 16;
     const size_t bytes = doubles * sizeof(double);
     static bool attr_set = false;

@@ -44,7 +44,11 @@ def _ptr(t):
     if t is None:
         return None
     if isinstance(t, np.ndarray):
+        if not t.flags["C_CONTIGUOUS"]:
+            raise ValueError("the C ABI takes contiguous buffers (got a strided numpy view)")
         return t.ctypes.data_as(C.c_void_p)
+    if not t.is_contiguous():
+        raise ValueError("the C ABI takes contiguous buffers (got a strided tensor view; call .contiguous())")
     return C.c_void_p(t.data_ptr())
 
 

