@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--samples", type=int, default=N_PER_GPU, help="samples per GPU (default: the C3 workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option for A/B measurements (bsde_ctx_set_option), e.g. fuse_interface=0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,6 +199,9 @@ def main():
     be = get_backend()
     if world > 1:
         be.init_distributed()
+    for kv in args.option:
+        name, _, val = kv.partition("=")
+        be.set_option(name, int(val))
     N = args.samples
 
     # ---- synthetic workload, generated on the device by the library's own kernels ----

@@ -98,6 +98,7 @@ struct bsde_ctx {
     DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg, clk;
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
+    int64_t fuse_interface = 1;   // option: ALS forms the trailing interface inside the next assembly kernel (als_sweep)
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     // per-kernel-class device timing (option "profile"): event pairs recorded around eager launches
@@ -333,16 +334,24 @@ struct SalsaReg {            // als.py:143-174, all device pointers
 };
 
 int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridge, const double* reg_diag, double* dbg,
-               const SalsaReg* sr = nullptr) {
+               const SalsaReg* sr = nullptr, const FusedInterface* fi = nullptr) {
     const Train& T = *m.T;
     const int rl = T.ranks[j], rr = T.ranks[j + 1];
     const AsmPlan* P;
     BSDE_TRY(get_plan(c, rl, T.p, rr, m.mono, m.in->N, &P));
     BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
     BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride));
+    if (fi && fi->side && !asm_fuse_supported(*P, *m.in, *fi)) {      // this shape cannot fuse: separate interface kernel
+        cudaEvent_t i0 = prof_mark(c);
+        if (fi->side == 1) BSDE_TRY(launch_interface_left(*m.in, fi->j, fi->core, fi->r_in, rl, fi->in, fi->out, c->stream));
+        else BSDE_TRY(launch_interface_right(*m.in, fi->j, fi->core, rr, fi->r_in, fi->in, fi->out, c->stream));
+        c->launches++;
+        prof_span(c, bsde_ctx::P_INTERFACE, i0, prof_mark(c));
+        fi = nullptr;
+    }
     cudaEvent_t e0 = prof_mark(c), e1 = prof_take(c);
     BSDE_TRY(launch_assembly(*P, *m.in, j, j == 0 ? nullptr : m.B->at(j), j == T.d - 1 ? nullptr : m.B->at(j + 1), m.y,
-                             c->partial.as<double>(), c->moments.as<double>(), c->stream, e1, c->px_on ? &c->px : nullptr));
+                             c->partial.as<double>(), c->moments.as<double>(), c->stream, e1, c->px_on ? &c->px : nullptr, fi));
     c->launches += 2;
     cudaEvent_t e2 = prof_mark(c);
     prof_span(c, bsde_ctx::P_ASSEMBLY, e0, e1);
@@ -375,11 +384,34 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     return 0;
 }
 
-// one ALS sweep: als.py:61-94
-int als_sweep(bsde_ctx* c, const MicroCtx& m) {
+// one ALS sweep: als.py:61-94.
+// fused = 0: every micro-step is followed by its own interface kernel (explicit basis values, option "fuse_interface" 0).
+// fused = 1: the interface a micro-step leaves behind is formed inside the assembly kernel of the NEXT micro-step
+//            (FusedInterface); `first` = this is the first sweep of the fit (the right interfaces were built up front,
+//            so core 0 has nothing to fuse).  After the last micro-step (j = 1) no interface is needed any more.
+int als_sweep(bsde_ctx* c, const MicroCtx& m, int fused = 0, int first = 1) {
     const Train& T = *m.T;
     const int d = T.d;
+    auto left_of = [&](int j) {          // L_j from core j-1
+        FusedInterface f;
+        f.side = 1; f.j = j - 1; f.r_in = T.ranks[j - 1]; f.core = T.core(j - 1);
+        f.in = j - 1 == 0 ? nullptr : m.B->at(j - 1); f.out = m.B->at(j);
+        return f;
+    };
+    auto right_of = [&](int j) {         // R_j from core j+1
+        FusedInterface f;
+        f.side = 2; f.j = j + 1; f.r_in = T.ranks[j + 2]; f.core = T.core(j + 1);
+        f.in = j + 1 == d - 1 ? nullptr : m.B->at(j + 2); f.out = m.B->at(j + 1);
+        return f;
+    };
     for (int j = 0; j < d - 1; j++) {
+        if (fused) {
+            FusedInterface f;
+            if (j > 0) f = left_of(j);
+            else if (!first) f = right_of(0);
+            BSDE_TRY(micro_step(c, m, j, +1, 0.0, nullptr, nullptr, nullptr, &f));
+            continue;
+        }
         BSDE_TRY(micro_step(c, m, j, +1, 0.0, nullptr, nullptr));
         cudaEvent_t e0 = prof_mark(c);
         BSDE_TRY(launch_interface_left(*m.in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == 0 ? nullptr : m.B->at(j),
@@ -388,6 +420,11 @@ int als_sweep(bsde_ctx* c, const MicroCtx& m) {
         prof_span(c, bsde_ctx::P_INTERFACE, e0, prof_mark(c));
     }
     for (int j = d - 1; j >= 1; j--) {
+        if (fused) {
+            const FusedInterface f = j == d - 1 ? left_of(j) : right_of(j);
+            BSDE_TRY(micro_step(c, m, j, -1, 0.0, nullptr, nullptr, nullptr, &f));
+            continue;
+        }
         BSDE_TRY(micro_step(c, m, j, -1, 0.0, nullptr, nullptr));
         cudaEvent_t e0 = prof_mark(c);
         BSDE_TRY(launch_interface_right(*m.in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == d - 1 ? nullptr : m.B->at(j + 1),
@@ -440,7 +477,8 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
         BSDE_TRY(build_right(c, T, in, B, 1));
         MicroCtx m{&T, &in, &B, y_dev, solver_id, basis_kind == BASIS_POLY ? 1 : 0, info};
         int it = 0;
-        if (n_iter > 0) { BSDE_TRY(als_sweep(c, m)); it = 1; }     // also builds the assembly plans / workspaces
+        const int fused = (c->fuse_interface && basis_kind != BASIS_PHI) ? 1 : 0;
+        if (n_iter > 0) { BSDE_TRY(als_sweep(c, m, fused, 1)); it = 1; }     // also builds the assembly plans / workspaces
         if (it < n_iter) {
             if (c->use_graph && !c->profile && n_iter - it >= 2) {
                 cudaGraph_t graph = nullptr;
@@ -448,7 +486,7 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
                 const int64_t before = c->launches;
                 BSDE_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                 c->capturing = true;
-                const int rc = als_sweep(c, m);
+                const int rc = als_sweep(c, m, fused, 0);
                 c->capturing = false;
                 cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
                 if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -466,7 +504,7 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) return fail_cuda(e, "cudaGraphLaunch", __FILE__, __LINE__);
             } else {
-                for (; it < n_iter; it++) BSDE_TRY(als_sweep(c, m));
+                for (; it < n_iter; it++) BSDE_TRY(als_sweep(c, m, fused, 0));
             }
         }
     }
@@ -687,6 +725,7 @@ int bsde_ctx_launch_count(bsde_ctx* c, int64_t* out) {
 int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     BSDE_CHECK_CTX(c);
     if (name && !strcmp(name, "use_graph")) { c->use_graph = value; return 0; }
+    if (name && !strcmp(name, "fuse_interface")) { c->fuse_interface = value; return 0; }
     if (name && !strcmp(name, "asm_generic")) {
         c->asm_generic = value;
         for (auto& kv : c->plans) asm_plan_free(kv.second);

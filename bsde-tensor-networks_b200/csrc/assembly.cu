@@ -60,6 +60,18 @@ struct AsmArgs {
     int tab_entries;             // register-blocked: uint16 entries to copy into shared memory
     double* partial;
     int64_t partial_stride;
+    // fused interface update (FusedInterface, kernels.cuh): the interface on the side the sweep comes from is not read
+    // from a.L / a.R but formed from the neighbouring bond, the neighbouring core and that asset's basis, and written
+    // back as a by-product
+    int fuse;                    // 0 none, 1 left (a.L is the OUTPUT), 2 right (a.R is the OUTPUT)
+    int fj, fr_in;               // asset of the neighbouring core; components of f_in
+    const double* fcore;
+    const double* f_in;          // neighbouring bond, null = ones(1)
+    double* f_out;
+    int core_off;                // shared-memory offset (doubles) of the staged neighbouring core
+    const double* ldL;           // what load_raw reads into RawSample::L / R, and how many components
+    const double* ldR;
+    int nldL, nldR;
 };
 
 // volatile: keeps the DMMAs of one k-step together in program order (independent accumulators back to back)
@@ -76,6 +88,7 @@ template <int RB, int PB>
 struct RawSample {
     double L[RB], R[RB], y, vm;
     double xb[PB];      // xb[0] = x (fused bases) or the p explicit basis values
+    double xf;          // fused interface update: x of the neighbouring asset
 };
 
 template <int RB, int PB>
@@ -86,11 +99,14 @@ __device__ __forceinline__ void load_raw(const AsmArgs& a, int lane, int64_t chu
     const bool valid = s < N;
     const int64_t sc = valid ? s : N - 1;
     r.vm = valid ? 1.0 : 0.0;
+    // (a.ldL, a.ldR: the bonds the raw loads come from — with a fused update one of them is the NEIGHBOURING bond, which
+    // fuse_interface turns into this core's interface; selected on the host so that nothing here depends on loaded data)
 #pragma unroll
     for (int q = 0; q < RB; q++) {
-        r.L[q] = (q < a.rl) ? (a.L ? a.L[(int64_t)q * N + sc] : 1.0) : 0.0;
-        r.R[q] = (q < a.rr) ? (a.R ? a.R[(int64_t)q * N + sc] : 1.0) : 0.0;
+        r.L[q] = (q < a.nldL) ? (a.ldL ? a.ldL[(int64_t)q * N + sc] : 1.0) : 0.0;
+        r.R[q] = (q < a.nldR) ? (a.ldR ? a.ldR[(int64_t)q * N + sc] : 1.0) : 0.0;
     }
+    if (a.fuse) r.xf = a.in.data[(int64_t)a.fj * N + sc];
     r.y = a.y[sc];
     if (a.in.kind == BASIS_PHI) {
         const double* src = a.in.data + ((int64_t)a.j * a.in.p) * N + sc;
@@ -98,6 +114,118 @@ __device__ __forceinline__ void load_raw(const AsmArgs& a, int lane, int64_t chu
         for (int m = 0; m < PB; m++) r.xb[m] = (m < a.in.p) ? src[(int64_t)m * N] : 0.0;
     } else {
         r.xb[0] = a.in.data[(int64_t)a.j * N + sc];
+    }
+}
+
+// Fused interface update, bit-identical to k_interface_left / k_interface_right (interface.cu: same basis routine, same
+// order of the FMAs):  left   L_j[b]     = sum_{a,m} (L_{j-1}[a] phi_{j-1}[m]) C_{j-1}[a,m,b]
+//                      right  R_j[a]     = sum_m phi_{j+1}[m] (sum_b C_{j+1}[a,m,b] R_{j+1}[b])
+// The result replaces the raw neighbouring bond in r and is stored for the micro-steps that follow.
+template <int RB, int PB>
+__device__ __forceinline__ void fuse_interface(const AsmArgs& a, const double* __restrict__ core, int64_t s,
+                                               RawSample<RB, PB>& r) {
+    double phi[PB];
+    double out[RB];
+    // full interior shape (monomials, p = PB, both bond ranks = RB): straight-line code, the core read as 16-byte
+    // broadcasts — the C3 hot path; every other shape takes the predicated general form below
+    if (a.in.kind == BASIS_POLY && a.in.p == PB && a.fr_in == RB && (a.fuse == 1 ? a.rl : a.rr) == RB) {
+        monomials_cr<PB>(r.xf, phi);
+        const double2* c2 = reinterpret_cast<const double2*>(core);
+        if (a.fuse == 1) {
+#pragma unroll
+            for (int b = 0; b < RB; b++) out[b] = 0.0;
+#pragma unroll
+            for (int q = 0; q < RB; q++)
+#pragma unroll
+                for (int m = 0; m < PB; m++) {
+                    const double t = r.L[q] * phi[m];
+#pragma unroll
+                    for (int b = 0; b < RB; b += 2) {
+                        const double2 cv = c2[((q * PB + m) * RB + b) >> 1];
+                        out[b] = fma(t, cv.x, out[b]);
+                        out[b + 1] = fma(t, cv.y, out[b + 1]);
+                    }
+                }
+#pragma unroll
+            for (int b = 0; b < RB; b++) {
+                r.L[b] = out[b];
+                if (r.vm != 0.0) a.f_out[(int64_t)b * a.in.N + s] = out[b];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < PB; m++) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int b = 0; b < RB; b += 2) {
+                        const double2 cv = c2[((q * PB + m) * RB + b) >> 1];
+                        t = fma(cv.x, r.R[b], t);
+                        t = fma(cv.y, r.R[b + 1], t);
+                    }
+                    acc = fma(phi[m], t, acc);
+                }
+                out[q] = acc;
+            }
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                r.R[q] = out[q];
+                if (r.vm != 0.0) a.f_out[(int64_t)q * a.in.N + s] = out[q];
+            }
+        }
+        return;
+    }
+    basis_from_x<PB>(a.in, r.xf, 0, phi);
+    const int p = a.in.p;
+    if (a.fuse == 1) {
+        const int r_out = a.rl;
+#pragma unroll
+        for (int b = 0; b < RB; b++) out[b] = 0.0;
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            if (q >= a.fr_in) break;
+#pragma unroll
+            for (int m = 0; m < PB; m++) {
+                if (m < p) {
+                    const double* c = core + (q * p + m) * r_out;
+                    const double t = r.L[q] * phi[m];
+#pragma unroll
+                    for (int b = 0; b < RB; b++)
+                        if (b < r_out) out[b] = fma(t, c[b], out[b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < RB; b++) {
+            r.L[b] = (b < r_out) ? out[b] : 0.0;
+            if (b < r_out && r.vm != 0.0) a.f_out[(int64_t)b * a.in.N + s] = out[b];
+        }
+    } else {
+        const int r_out = a.rr;
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            double acc = 0.0;
+            if (q < r_out) {
+#pragma unroll
+                for (int m = 0; m < PB; m++) {
+                    if (m < p) {
+                        const double* c = core + (q * p + m) * a.fr_in;
+                        double t = 0.0;
+#pragma unroll
+                        for (int b = 0; b < RB; b++)
+                            if (b < a.fr_in) t = fma(c[b], r.R[b], t);
+                        acc = fma(phi[m], t, acc);
+                    }
+                }
+            }
+            out[q] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            r.R[q] = (q < r_out) ? out[q] : 0.0;
+            if (q < r_out && r.vm != 0.0) a.f_out[(int64_t)q * a.in.N + s] = out[q];
+        }
     }
 }
 
@@ -205,6 +333,11 @@ k_assemble_rb(AsmArgs a) {
     double* ws = sm + (size_t)warp * a.warp_doubles;
     unsigned short* stab = reinterpret_cast<unsigned short*>(sm + (size_t)kAsmWarps * a.warp_doubles);
     for (int e = threadIdx.x; e < a.tab_entries; e += kAsmThreads) stab[e] = (unsigned short)(a.tab[e] * kStride);
+    const double* score = sm + a.core_off;
+    if (a.fuse) {
+        const int nc = (a.fuse == 1 ? a.fr_in * a.rl : a.rr * a.fr_in) * a.in.p;
+        for (int e = threadIdx.x; e < nc; e += kAsmThreads) sm[a.core_off + e] = a.fcore[e];
+    }
     __syncthreads();
     const int g8 = lane >> 2;
     // per-lane fragment sources (offsets in doubles): row tiles of M1 then of M2, two factors each; column tiles
@@ -236,6 +369,7 @@ k_assemble_rb(AsmArgs a) {
     RawSample<RB, PB> raw;
     load_raw<RB, PB>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
     for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
+        if (a.fuse) fuse_interface<RB, PB>(a, score, chunk * 32 + lane, raw);
         accyy += stage_functions<RB, PB>(a, ws, lane, raw);
         load_raw<RB, PB>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
         __syncwarp();
@@ -275,6 +409,124 @@ k_assemble_rb(AsmArgs a) {
         __syncwarp();
     }
     write_partials<NT>(a, sm, ws, acc, accyy, lane, 0, true);
+}
+
+// =====================================================================================================
+// rank-4 / 4-monomial variant ("RR-stationary"): the interior cores of the C3..C5 workloads (r_l = r_r = p = 4)
+// =====================================================================================================
+// k_assemble_rb needs two shared-memory fragment loads per DMMA (the two factors of the A fragment), 660 shared-memory
+// wavefronts per 32-sample chunk — ncu: the LSU pipe is 76 % busy, which is what caps its DMMA rate at 59 %.  This
+// variant arranges the 100 rows (lambda, rho) of M1 so that almost every operand is reused from registers:
+//
+//   tile lambda = 0..9 :  row g = rho = 0..7                     A = RR_g(s) * LL_lambda(s)
+//   tile 10, 11        :  row g = lambda = 0..7, rho = 8 | 9      A = LL_g(s) * RR_8|9(s)
+//   tile 12            :  row g < 4: lambda = 8 + g/2, rho = 8 + g%2
+//   tile 13, 14 (M2)   :  row g: a = 2 (tile - 13) + g/4, b = g%4  A = L_a(s) * R_b(s),  B = (phi_m y)(s)
+//
+// (g = lane / 4 = row of the fragment, s = the lane's sample of the k-step).  RR_g, LL_g, R_b and the two B fragments
+// are one fragment load per k-step each; RR_8, RR_9 and L_0..3 depend on the sample only, are staged sample-major and
+// read with 3 LDS.128 per k-step (a 16-byte load costs 4 wavefronts however few distinct addresses it has, which is why
+// LL_lambda(s) = L_a(s) L_a'(s) is formed in registers as (RR_g L_a) L_a' rather than broadcast from shared memory).
+// 8 shared-memory instructions and 22 wavefronts per k-step of 15 DMMAs instead of 32 and 64.
+constexpr int kR4Tiles = 15;
+constexpr int kR4FmRows = 32;            // function-major rows: RR_0..7 | B_0..6, ZERO | LL_0..7 | R_0..3 | phi_m y
+constexpr int kR4SmStride = 10;          // sample-major doubles per sample: RR_8, RR_9, L_0..3, 4 pad (conflict-free 16-byte reads)
+constexpr int kR4WarpDoubles = kR4FmRows * kStride + 32 * kR4SmStride;
+
+__global__ void __launch_bounds__(kAsmThreads, 3)
+k_assemble_r4(AsmArgs a) {
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* ws = sm + (size_t)warp * a.warp_doubles;
+    double* wsm = ws + kR4FmRows * kStride;
+    const double* score = sm + a.core_off;
+    if (a.fuse) {
+        const int nc = (a.fuse == 1 ? a.fr_in * a.rl : a.rr * a.fr_in) * a.in.p;
+        for (int e = threadIdx.x; e < nc; e += kAsmThreads) sm[a.core_off + e] = a.fcore[e];
+    }
+    ws[15 * kStride + lane] = 0.0;       // the ZERO function (samples 0..31 are all that is ever read)
+    __syncthreads();
+    const int g = lane >> 2;
+    // per-lane fragment sources
+    const double* fm = ws + (lane & 3);
+    const int o_rr = g * kStride, o_bf = (8 + g) * kStride, o_llg = (16 + g) * kStride, o_rb = (24 + (g & 3)) * kStride;
+    const int o_fy = (g < 4 ? 28 + g : 15) * kStride;
+    const double2* smp = reinterpret_cast<const double2*>(wsm + (lane & 3) * kR4SmStride);
+    const bool hi = (g & 4) != 0;        // M2 tiles: a = 2 t + (g >> 2)
+    const bool t12 = g < 4, t12l = (g & 2) != 0, t12r = (g & 1) != 0;
+
+    double acc[kR4Tiles][2];
+#pragma unroll
+    for (int t = 0; t < kR4Tiles; t++) acc[t][0] = acc[t][1] = 0.0;
+    double accyy = 0.0;
+
+    const int64_t nchunks = (a.in.N + 31) / 32;
+    const int64_t warps_total = (int64_t)gridDim.x * kAsmWarps;
+    RawSample<4, 4> raw;
+    load_raw<4, 4>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
+    for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
+        if (a.fuse) fuse_interface<4, 4>(a, score, chunk * 32 + lane, raw);
+        {   // ---- phase 1: lane = sample ----
+            const double vm = raw.vm, yv = raw.y * vm;
+            double ll[10], rr[10];
+            int idx = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int q2 = q; q2 < 4; q2++) { ll[idx] = raw.L[q] * raw.L[q2]; rr[idx] = raw.R[q] * raw.R[q2]; idx++; }
+            double2* srow = reinterpret_cast<double2*>(wsm + lane * kR4SmStride);
+            srow[0] = make_double2(rr[8], rr[9]);
+            srow[1] = make_double2(raw.L[0], raw.L[1]);
+            srow[2] = make_double2(raw.L[2], raw.L[3]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                ws[k * kStride + lane] = rr[k];
+                ws[(16 + k) * kStride + lane] = ll[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) ws[(24 + k) * kStride + lane] = raw.R[k];
+            const double x = raw.xb[0];
+            double pw = vm;
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                ws[(8 + k) * kStride + lane] = pw;
+                if (k < 4) ws[(28 + k) * kStride + lane] = pw * yv;
+                pw *= x;
+            }
+            accyy += yv * yv;
+        }
+        load_raw<4, 4>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
+        __syncwarp();
+        // ---- phase 2: 8 k-steps of 4 samples, 15 DMMA each ----
+#pragma unroll
+        for (int step = 0; step < 8; step++) {
+            const double* w = fm + step * 4;
+            const double2* sp = smp + step * (4 * kR4SmStride / 2);
+            const double rrg = w[o_rr], bf = w[o_bf], llg = w[o_llg], rb = w[o_rb], fy = w[o_fy];
+            const double2 r89 = sp[0], s01 = sp[1], s23 = sp[2];
+            // A fragment of tile lambda = (a, a'):  (RR_g L_a) L_a'  — 4 + 10 products from the 4 interface components
+            // instead of 10 products from 10 broadcast LL values (shared-memory wavefronts are the scarcer resource)
+            const double u0 = rrg * s01.x, u1 = rrg * s01.y, u2 = rrg * s23.x, u3 = rrg * s23.y;
+            dmma884(acc[0][0], acc[0][1], u0 * s01.x, bf);
+            dmma884(acc[1][0], acc[1][1], u0 * s01.y, bf);
+            dmma884(acc[2][0], acc[2][1], u0 * s23.x, bf);
+            dmma884(acc[3][0], acc[3][1], u0 * s23.y, bf);
+            dmma884(acc[4][0], acc[4][1], u1 * s01.y, bf);
+            dmma884(acc[5][0], acc[5][1], u1 * s23.x, bf);
+            dmma884(acc[6][0], acc[6][1], u1 * s23.y, bf);
+            dmma884(acc[7][0], acc[7][1], u2 * s23.x, bf);
+            dmma884(acc[8][0], acc[8][1], u2 * s23.y, bf);
+            dmma884(acc[9][0], acc[9][1], u3 * s23.y, bf);
+            dmma884(acc[10][0], acc[10][1], llg * r89.x, bf);
+            dmma884(acc[11][0], acc[11][1], llg * r89.y, bf);
+            const double c12 = t12 ? (t12l ? s23.y : s23.x) * s23.y : 0.0;          // LL_8 = L_2 L_3, LL_9 = L_3 L_3
+            dmma884(acc[12][0], acc[12][1], c12 * (t12r ? r89.y : r89.x), bf);
+            dmma884(acc[13][0], acc[13][1], (hi ? s01.y : s01.x) * rb, fy);
+            dmma884(acc[14][0], acc[14][1], (hi ? s23.y : s23.x) * rb, fy);
+        }
+        __syncwarp();
+    }
+    write_partials<kR4Tiles>(a, sm, ws, acc, accyy, lane, 0, true);
 }
 
 // =====================================================================================================
@@ -320,6 +572,11 @@ k_assemble(AsmArgs a) {
         stab[e] = (unsigned long long)(t[0] * kStride) | ((unsigned long long)(t[1] * kStride) << 16) |
                   ((unsigned long long)(t[2] * kStride) << 32);
     }
+    const double* score = sm + a.core_off;
+    if (a.fuse) {
+        const int nc = (a.fuse == 1 ? a.fr_in * a.rl : a.rr * a.fr_in) * a.in.p;
+        for (int e = threadIdx.x; e < nc; e += kAsmThreads) sm[a.core_off + e] = a.fcore[e];
+    }
     __syncthreads();
     const unsigned long long* mytab = stab + (lane >> 2);
 
@@ -333,6 +590,8 @@ k_assemble(AsmArgs a) {
     RawSample<RB, PB> raw;
     load_raw<RB, PB>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
     for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
+        // (with several tile groups every group computes the same interface and stores identical values)
+        if (a.fuse) fuse_interface<RB, PB>(a, score, chunk * 32 + lane, raw);
         accyy += stage_functions<RB, PB>(a, ws, lane, raw);
         load_raw<RB, PB>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
         __syncwarp();
@@ -423,8 +682,11 @@ int run_kernel(K kernel, int op, const AsmPlan& plan, const AsmArgs* args, cudaS
     return 0;
 }
 
+constexpr int kRbClassR4 = 100;       // AsmPlan::rb_class of k_assemble_r4
+
 template <int RB, int PB>
 int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* occ) {
+    if (P.rb_class == kRbClassR4) return run_kernel(k_assemble_r4, op, P, a, st, occ);
     if (P.rb_class >= 0) {
         switch (P.rb_class) {
             case 0: return run_kernel(k_assemble_rb<1, 1, 1, RB, PB>, op, P, a, st, occ);
@@ -442,7 +704,8 @@ int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, i
 }
 
 int dispatch(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* occ) {
-    const int rb = std::max(P.rl, P.rr);
+    int rb = std::max(P.rl, P.rr);
+    if (a && a->fuse) rb = std::max(rb, a->fr_in);      // the fused update holds the neighbouring bond in the same registers
     const bool p4 = P.p <= 4;
     if (rb <= 4) return p4 ? dispatch_rbpb<4, 4>(op, P, a, st, occ) : dispatch_rbpb<4, 8>(op, P, a, st, occ);
     return p4 ? dispatch_rbpb<8, 4>(op, P, a, st, occ) : dispatch_rbpb<8, 8>(op, P, a, st, occ);
@@ -483,7 +746,8 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
     // The layout and tile-count class with the fewest DMMA tiles is chosen.
     P.rb_class = -1;
     int layout = 0;
-    if (!force_generic) {
+    const bool use_r4 = force_generic == 0 && rl == 4 && rr == 4 && p == 4 && mono;      // force_generic 2: rb classes only
+    if (force_generic != 1 && !use_r4) {
         int best_tiles = 1 << 30;
         for (int lay = 0; lay < 2; lay++) {
             const int rows1 = lay == 0 ? P.nB * P.nLL : P.nLL * P.nRR, cols1 = lay == 0 ? P.nRR : P.nB;
@@ -499,7 +763,27 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
         }
     }
 
-    if (P.rb_class >= 0) {
+    if (use_r4) {
+        // k_assemble_r4: see the tile layout in its header comment
+        P.rb_class = kRbClassR4;
+        n_tiles = kR4Tiles;
+        P.NJ = n_tiles; P.n_groups = 1; P.n_jobs = n_tiles;
+        for (int beta = 0; beta < P.nB; beta++)
+            for (int lam = 0; lam < P.nLL; lam++)
+                for (int rho = 0; rho < P.nRR; rho++) {
+                    int tile, row;
+                    if (rho < 8) { tile = lam; row = rho; }
+                    else if (lam < 8) { tile = 10 + (rho - 8); row = lam; }
+                    else { tile = 12; row = (lam - 8) * 2 + (rho - 8); }
+                    P.h_gather[((size_t)beta * P.nLL + lam) * P.nRR + rho] = tile * 64 + row * 8 + beta;
+                }
+        for (int m = 0; m < p; m++)
+            for (int a = 0; a < rl; a++)
+                for (int b = 0; b < rr; b++)
+                    P.h_gather[base2 + ((size_t)m * rl + a) * rr + b] = (13 + (a >> 1)) * 64 + ((a & 1) * 4 + b) * 8 + m;
+        P.tab_entries = 0;
+        tab_smem = 0;
+    } else if (P.rb_class >= 0) {
         const int RT1 = kRbClasses[P.rb_class][0], CT1 = kRbClasses[P.rb_class][1], RT2 = kRbClasses[P.rb_class][2];
         n_tiles = RT1 * CT1 + RT2;
         P.NJ = n_tiles; P.n_groups = 1; P.n_jobs = n_tiles;
@@ -593,7 +877,9 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
 
     const int tiles_per_cta = P.rb_class >= 0 ? n_tiles : P.NJ;
     P.warp_doubles = std::max(P.F * kStride + 16, tiles_per_cta * 64 + 1);    // +16: look-ahead reads of the pipelined loop
-    P.smem_bytes = (size_t)kAsmWarps * P.warp_doubles * sizeof(double) + ((tab_smem + 15) & ~(size_t)15);
+    if (use_r4) P.warp_doubles = std::max(kR4WarpDoubles, kR4Tiles * 64 + 2);
+    P.core_off = (int)((size_t)kAsmWarps * P.warp_doubles + (((tab_smem + 15) & ~(size_t)15) / sizeof(double)));
+    P.smem_bytes = ((size_t)P.core_off + (size_t)8 * kMaxP * 8) * sizeof(double);      // + the neighbouring core of a fused interface update
     if (P.smem_bytes > 200 * 1024) return fail_msg(2, "assembly: core shape (%d,%d,%d) needs %zu B of shared memory", rl, p, rr, P.smem_bytes);
     const int64_t nchunks = (N + 31) / 32;
     const int64_t want = (nchunks + kAsmWarps - 1) / kAsmWarps;
@@ -628,6 +914,13 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
     return 0;
 }
 
+bool asm_fuse_supported(const AsmPlan& P, const Inputs& in, const FusedInterface& fi) {
+    if (in.kind == BASIS_PHI) return false;
+    if (fi.r_in < 1 || fi.r_in > 8) return false;
+    if (P.rb_class == kRbClassR4 && fi.r_in > 4) return false;     // that kernel holds interfaces of at most 4 components
+    return true;
+}
+
 void asm_plan_free(AsmPlan& P) {
     if (P.d_tab) cudaFree(P.d_tab);
     if (P.d_gather) cudaFree(P.d_gather);
@@ -636,9 +929,19 @@ void asm_plan_free(AsmPlan& P) {
 }
 
 int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, const double* R, const double* y,
-                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid, const PeerExchange* px) {
+                    double* partial, double* moments, cudaStream_t st, cudaEvent_t mid, const PeerExchange* px,
+                    const FusedInterface* fi) {
     AsmArgs a;
     a.in = in; a.j = j; a.L = L; a.R = R; a.y = y;
+    a.fuse = 0; a.fj = 0; a.fr_in = 0; a.fcore = nullptr; a.f_in = nullptr; a.f_out = nullptr; a.core_off = P.core_off;
+    if (fi && fi->side) {
+        if (in.kind == BASIS_PHI) return fail_msg(2, "assembly: the fused interface update needs a fused basis (x inputs)");
+        if (fi->r_in < 1 || fi->r_in > 8 || !fi->core || !fi->out) return fail_msg(2, "assembly: bad fused interface update");
+        a.fuse = fi->side; a.fj = fi->j; a.fr_in = fi->r_in; a.fcore = fi->core; a.f_in = fi->in; a.f_out = fi->out;
+        if (fi->side == 1) a.L = fi->out; else a.R = fi->out;     // (documentation only: the kernel forms them itself)
+    }
+    a.ldL = a.fuse == 1 ? a.f_in : L; a.nldL = a.fuse == 1 ? a.fr_in : P.rl;
+    a.ldR = a.fuse == 2 ? a.f_in : R; a.nldR = a.fuse == 2 ? a.fr_in : P.rr;
     a.rl = P.rl; a.rr = P.rr; a.mono = P.mono; a.nB = P.nB;
     a.F = P.F; a.fLL = P.fLL; a.fRR = P.fRR; a.fRow1 = P.fRow1; a.fL = P.fL; a.fR = P.fR; a.fRow2 = P.fRow2;
     a.warp_doubles = P.warp_doubles;

@@ -34,6 +34,7 @@ struct AsmPlan {
     int64_t partial_stride = 0;                   // doubles per partial row = tiles*64 + 1
     int warp_doubles = 0;                         // shared-memory doubles per warp
     int tab_entries = 0;
+    int core_off = 0;                             // shared-memory offset (doubles) of the fused update's neighbouring core
     size_t smem_bytes = 0;
     uint16_t* d_tab = nullptr;                    // fragment-source table (layout depends on the variant)
     int32_t* d_gather = nullptr;                  // [n_mom] canonical moment -> slot in a partial row
@@ -54,13 +55,26 @@ struct PeerExchange {
     int* error = nullptr;                          // local    : set to 1 when a wait timed out
 };
 
+// Interface update fused into the assembly of the NEXT micro-step of an ALS half-sweep: the kernel forms the interface
+// on the side the sweep comes from out of the neighbouring bond, core and asset instead of reading it, and writes it to
+// `out` (it is needed again by the later micro-steps).  Bit-identical to k_interface_left / k_interface_right.
+struct FusedInterface {
+    int side = 0;                 // 0 none; 1 left: L_j from core j-1; 2 right: R_j from core j+1
+    int j = 0;                    // asset of the neighbouring core
+    int r_in = 1;                 // components of `in`
+    const double* core = nullptr; // neighbouring core, (r_in, p, r_l) for side 1, (r_r, p, r_in) for side 2
+    const double* in = nullptr;   // neighbouring bond, null = ones(1)
+    double* out = nullptr;        // receives the interface (r_l resp. r_r components)
+};
+
 int asm_plan_build(AsmPlan& plan, int rl, int p, int rr, int mono, int64_t N, int sm_count, int force_generic = 0);
 void asm_plan_free(AsmPlan& plan);
+bool asm_fuse_supported(const AsmPlan& plan, const Inputs& in, const FusedInterface& fi);
 // Launches the assembly kernel and the partial reduction; `moments` (n_mom doubles, device) receives
 // [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y].
 int launch_assembly(const AsmPlan& plan, const Inputs& in, int j, const double* L, const double* R, const double* y,
                     double* partial, double* moments, cudaStream_t st, cudaEvent_t mid = nullptr,
-                    const PeerExchange* px = nullptr);
+                    const PeerExchange* px = nullptr, const FusedInterface* fi = nullptr);
 
 // ---- dense.cu ------------------------------------------------------------------------------------
 enum SolverId : int { SOLVER_LSTSQ = 0, SOLVER_LU = 1, SOLVER_QR = 2, SOLVER_SOLVE = 3 };

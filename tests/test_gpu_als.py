@@ -137,6 +137,44 @@ def test_als_matches_oracle_on_fresh_inputs(backend):
         backend.set_option("use_graph", 1)
 
 
+def test_fused_interface_update_is_bit_identical(backend):
+    """ALS forms the interface a micro-step leaves behind inside the NEXT assembly kernel (FusedInterface, assembly.cu).
+    It must give exactly the bits of the separate interface kernels: same cores after the fit, eager and graph."""
+    from bsde_solver._backend import DeviceInputs
+    from bsde_solver._lib import BASIS_LEGENDRE, BASIS_POLY
+    from bsde_solver.core.calculus.basis import LegendreBasis
+
+    rng = np.random.RandomState(11)
+    for d, p, ranks, N, kind in ((2, 3, [1, 2, 1], 257, "poly"), (3, 4, [1, 4, 3, 1], 1000, "poly"),
+                                 (6, 4, [1, 4, 4, 4, 4, 4, 1], 40000, "poly"), (5, 3, [1, 2, 3, 3, 2, 1], 1531, "leg"),
+                                 (4, 5, [1, 3, 5, 3, 1], 2048, "poly"), (12, 4, [1] + [4] * 11 + [1], 70001, "poly")):
+        x = rng.randn(N, d) * 0.7
+        y = np.log(0.5 + 0.5 * (x**2).sum(axis=1)) + 0.1 * x[:, 0]
+        init = flat([rng.rand(ranks[i], p, ranks[i + 1]) * 2 - 1 for i in range(d)])
+        inp = DeviceInputs(BASIS_POLY if kind == "poly" else BASIS_LEGENDRE, p, backend.to_device(np.ascontiguousarray(x.T)),
+                           coef=None if kind == "poly" else LegendreBasis(p)._coef())
+        yd = backend.to_device(y)
+        out = {}
+        try:
+            for fuse in (0, 1):
+                for use_graph in (1, 0):
+                    backend.set_option("fuse_interface", fuse)
+                    backend.set_option("use_graph", use_graph)
+                    got = init.copy()
+                    n0 = backend.launch_count()
+                    backend.fit_als(inp, yd, 4, np.array(ranks, dtype=np.int32), 0, got)
+                    out[(fuse, use_graph)] = (got, backend.launch_count() - n0)
+        finally:
+            backend.set_option("fuse_interface", 1)
+            backend.set_option("use_graph", 1)
+        base = out[(0, 0)][0]
+        assert np.all(np.isfinite(base))
+        for key, (got, launches) in out.items():
+            assert np.array_equal(got, base), (d, p, kind, key)
+        # one launch fewer per micro-step (first sweep: the first micro-step has nothing to fuse)
+        assert out[(1, 1)][1] < out[(0, 1)][1]
+
+
 def test_step0_fit_returns_mean(backend):
     """at time step 0 all samples coincide, A has rank 1, lstsq's minimum-norm solution fits mean(y)."""
     from bsde_solver._backend import DeviceInputs
