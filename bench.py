@@ -283,7 +283,9 @@ def main():
     be.set_option("profile", 1)
     fit_device()
     stats = {k: (be.get_stat(f"{k}_ms"), int(be.get_stat(f"{k}_n"))) for k in ("assembly", "reduce", "allreduce", "solve", "interface")}
-    solve_phase_cycles = [be.get_stat(f"solve_phase{k}") for k in range(4)]
+    solve_phase_cycles = [be.get_stat(f"solve_phase{k}") for k in range(7)]
+    if os.environ.get("BSDE_SOLVE_TQ"):
+        print("solve tq", [be.get_stat(f"solve_phase{k}") / max(1, stats["solve"][1]) for k in range(8, 16)], file=sys.stderr)
     be.set_option("profile", 0)
     asm_ms, asm_n = stats["assembly"]
     n_int, n_edge = R * P * R, P * R
@@ -300,7 +302,7 @@ def main():
                 "note": "achieved counts the reference algorithm's n(n+1)+2n flops per sample; the kernel executes ~0.36x of them (Kronecker moment factorisation), so frac can exceed 1",
                 "share_of_step": {k: v[0] / total_prof for k, v in stats.items()},
                 "class_us_per_launch": {k: (1e3 * v[0] / v[1] if v[1] else None) for k, v in stats.items()},
-                "solve_kernel_phase_cycles_per_launch": dict(zip(("expand_moments", "solve", "qr", "push_factor"),
+                "solve_kernel_phase_cycles_per_launch": dict(zip(("expand_moments", "solve", "qr", "push_factor", "solve:load", "solve:factor", "solve:back_substitution"),
                                                                  [c / max(1, stats["solve"][1]) for c in solve_phase_cycles]))}
     try:
         with open(os.path.join(ROOT, "profiles", "assembly_traffic.json")) as f:

@@ -98,6 +98,8 @@ struct bsde_ctx {
     DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg, clk;
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
+    int64_t solve_stop = 0;       // measurement only (MicroSolveArgs::stop_after)
+    int64_t fast_solve = 1;       // option: register-resident fast kernel in front of k_micro_solve (dense.cu)
     int64_t fuse_interface = 1;   // option: ALS forms the trailing interface inside the next assembly kernel (als_sweep)
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -136,14 +138,18 @@ struct Guard {   // select the context's device for the duration of a call
 #define BSDE_CHECK_CTX(c) \
     if (!(c)) return fail_msg(2, "null context")
 
+// Called at the start of a fit only: a plan must never be dropped (and rebuilt with cudaMalloc) between the first sweep
+// of a fit and the capture of its sweep graph.
+void plans_trim(bsde_ctx* c) {
+    if (c->plans.size() <= 48) return;
+    for (auto& kv : c->plans) asm_plan_free(kv.second);
+    c->plans.clear();
+}
+
 int get_plan(bsde_ctx* c, int rl, int p, int rr, int mono, int64_t N, const AsmPlan** out) {
     auto key = std::make_tuple(rl, p, rr, mono, N);
     auto it = c->plans.find(key);
     if (it == c->plans.end()) {
-        if (c->plans.size() > 64) {
-            for (auto& kv : c->plans) asm_plan_free(kv.second);
-            c->plans.clear();
-        }
         AsmPlan P;
         BSDE_TRY(asm_plan_build(P, rl, p, rr, mono, N, c->sm_count, (int)c->asm_generic));
         it = c->plans.emplace(key, std::move(P)).first;
@@ -374,12 +380,15 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     if (direction < 0) { a.core_nb = T.core(j - 1); a.r_nb = T.ranks[j - 1]; }
     a.ridge = ridge; a.reg_diag = reg_diag; a.dbg_A = dbg; a.info = m.info;
     if (c->profile && !c->capturing) {
-        if (!c->clk.p) { if (c->clk.ensure(64) == 0) cudaMemset(c->clk.p, 0, 64); }
+        if (!c->clk.p) { if (c->clk.ensure(256) == 0) cudaMemset(c->clk.p, 0, 256); }
         a.clk = c->clk.as<long long>();
     }
     if (sr) { a.eta_ptr = sr->eta; a.gamma = sr->gamma; a.theta = sr->theta; a.reg_left = sr->reg_left; a.reg_right = sr->reg_right; }
-    BSDE_TRY(launch_micro_solve(a, c->stream));
-    c->launches++;
+    if (c->fast_solve && c->scalars.p) a.fast_flag = c->scalars.as<int>() + 24;
+    a.stop_after = (int)c->solve_stop;
+    int extra = 0;
+    BSDE_TRY(launch_micro_solve(a, c->stream, &extra));
+    c->launches += 1 + extra;
     prof_span(c, bsde_ctx::P_SOLVE, e3, prof_mark(c));
     return 0;
 }
@@ -455,6 +464,7 @@ int info_reset(bsde_ctx* c, int** info) {
 int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
             const double* y_dev, int n_iter, const int* ranks, int solver_id, double* cores_host, int* info_host) {
     BSDE_TRY(check_ranks(d, p, ranks));
+    plans_trim(c);
     if (!y_dev || !cores_host) return fail_msg(2, "fit_als: null y or cores pointer");
     if (n_iter < 0) return fail_msg(2, "fit_als: n_iter = %d", n_iter);
     if (solver_id < 0 || solver_id > 3) return fail_msg(2, "Unknown method %d", solver_id);
@@ -526,6 +536,7 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
               const double* y_dev, int n_iter, int* ranks, const int* init_ranks, double omega, double freq_omega, double min_sv,
               int max_rank, int solver_id, int do_reg, double* cores_host, int64_t cores_capacity, double* state_out_host) {
     BSDE_TRY(check_ranks(d, p, ranks));
+    plans_trim(c);
     if (!init_ranks) return fail_msg(2, "fit_salsa: init_ranks is null");
     if (!y_dev || !cores_host) return fail_msg(2, "fit_salsa: null y or cores pointer");
     if (solver_id < 0 || solver_id > 3) return fail_msg(2, "Unknown method %d", solver_id);
@@ -726,6 +737,8 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     BSDE_CHECK_CTX(c);
     if (name && !strcmp(name, "use_graph")) { c->use_graph = value; return 0; }
     if (name && !strcmp(name, "fuse_interface")) { c->fuse_interface = value; return 0; }
+    if (name && !strcmp(name, "fast_solve")) { c->fast_solve = value; return 0; }
+    if (name && !strcmp(name, "solve_stop")) { c->solve_stop = value; return 0; }
     if (name && !strcmp(name, "asm_generic")) {
         c->asm_generic = value;
         for (auto& kv : c->plans) asm_plan_free(kv.second);
@@ -735,7 +748,7 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     if (name && !strcmp(name, "profile")) {      // per-kernel-class event timing of eager launches; resets the counters
         c->profile = value;
         for (int k = 0; k < bsde_ctx::P_CLASSES; k++) { c->prof_ms[k] = 0.0; c->prof_n[k] = 0; }
-        if (c->clk.p) cudaMemset(c->clk.p, 0, 64);
+        if (c->clk.p) cudaMemset(c->clk.p, 0, 256);
         return 0;
     }
     return fail_msg(2, "unknown option '%s'", name ? name : "(null)");
@@ -752,10 +765,12 @@ int bsde_ctx_get_stat(bsde_ctx* c, const char* name, double* out) {
             if (!strcmp(name + n, "_n")) { *out = (double)c->prof_n[k]; return 0; }
         }
     }
-    if (!strncmp(name, "solve_phase", 11) && name[11] >= '0' && name[11] <= '3' && !name[12]) {
-        long long v[4] = {0, 0, 0, 0};
+    if (!strncmp(name, "solve_phase", 11) && name[11] >= '0' && name[11] <= '9') {
+        long long v[32] = {};
+        const int k = atoi(name + 11);
+        if (k < 0 || k >= 32) return fail_msg(2, "unknown stat '%s'", name);
         if (c->clk.p) BSDE_CUDA_OK(cudaMemcpy(v, c->clk.p, sizeof v, cudaMemcpyDeviceToHost));
-        *out = (double)v[name[11] - '0'];
+        *out = (double)v[k];
         return 0;
     }
     if (!strcmp(name, "sm_count")) { *out = c->sm_count; return 0; }

@@ -418,7 +418,7 @@ k_assemble_rb(AsmArgs a) {
 // wavefronts per 32-sample chunk — ncu: the LSU pipe is 76 % busy, which is what caps its DMMA rate at 59 %.  This
 // variant arranges the 100 rows (lambda, rho) of M1 so that almost every operand is reused from registers:
 //
-//   tile lambda = 0..9 :  row g = rho = 0..7                     A = RR_g(s) * LL_lambda(s)
+//   tile lambda = 0..9 :  row g = rho = 0..7                     A = RR_g(s) L_a(s),  B = B_g(s) L_a'(s)
 //   tile 10, 11        :  row g = lambda = 0..7, rho = 8 | 9      A = LL_g(s) * RR_8|9(s)
 //   tile 12            :  row g < 4: lambda = 8 + g/2, rho = 8 + g%2
 //   tile 13, 14 (M2)   :  row g: a = 2 (tile - 13) + g/4, b = g%4  A = L_a(s) * R_b(s),  B = (phi_m y)(s)
@@ -433,7 +433,10 @@ constexpr int kR4FmRows = 32;            // function-major rows: RR_0..7 | B_0..
 constexpr int kR4SmStride = 10;          // sample-major doubles per sample: RR_8, RR_9, L_0..3, 4 pad (conflict-free 16-byte reads)
 constexpr int kR4WarpDoubles = kR4FmRows * kStride + 32 * kR4SmStride;
 
-__global__ void __launch_bounds__(kAsmThreads, 3)
+#ifndef BSDE_R4_MIN_BLOCKS
+#define BSDE_R4_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kAsmThreads, BSDE_R4_MIN_BLOCKS)
 k_assemble_r4(AsmArgs a) {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -504,23 +507,26 @@ k_assemble_r4(AsmArgs a) {
             const double2* sp = smp + step * (4 * kR4SmStride / 2);
             const double rrg = w[o_rr], bf = w[o_bf], llg = w[o_llg], rb = w[o_rb], fy = w[o_fy];
             const double2 r89 = sp[0], s01 = sp[1], s23 = sp[2];
-            // A fragment of tile lambda = (a, a'):  (RR_g L_a) L_a'  — 4 + 10 products from the 4 interface components
-            // instead of 10 products from 10 broadcast LL values (shared-memory wavefronts are the scarcer resource)
+            // tile lambda = (a, a'):  A = RR_g L_a,  B = B_g L_a'  — 8 products feed 10 DMMAs (the FP64 pipe is shared by
+            // DMMA and DMUL, and a 16-byte broadcast load costs 4 wavefronts however few distinct addresses it has, so
+            // LL_lambda(s) is neither loaded nor multiplied out)
             const double u0 = rrg * s01.x, u1 = rrg * s01.y, u2 = rrg * s23.x, u3 = rrg * s23.y;
-            dmma884(acc[0][0], acc[0][1], u0 * s01.x, bf);
-            dmma884(acc[1][0], acc[1][1], u0 * s01.y, bf);
-            dmma884(acc[2][0], acc[2][1], u0 * s23.x, bf);
-            dmma884(acc[3][0], acc[3][1], u0 * s23.y, bf);
-            dmma884(acc[4][0], acc[4][1], u1 * s01.y, bf);
-            dmma884(acc[5][0], acc[5][1], u1 * s23.x, bf);
-            dmma884(acc[6][0], acc[6][1], u1 * s23.y, bf);
-            dmma884(acc[7][0], acc[7][1], u2 * s23.x, bf);
-            dmma884(acc[8][0], acc[8][1], u2 * s23.y, bf);
-            dmma884(acc[9][0], acc[9][1], u3 * s23.y, bf);
+            const double v0 = bf * s01.x, v1 = bf * s01.y, v2 = bf * s23.x, v3 = bf * s23.y;
+            dmma884(acc[0][0], acc[0][1], u0, v0);
+            dmma884(acc[1][0], acc[1][1], u0, v1);
+            dmma884(acc[2][0], acc[2][1], u0, v2);
+            dmma884(acc[3][0], acc[3][1], u0, v3);
+            dmma884(acc[4][0], acc[4][1], u1, v1);
+            dmma884(acc[5][0], acc[5][1], u1, v2);
+            dmma884(acc[6][0], acc[6][1], u1, v3);
+            dmma884(acc[7][0], acc[7][1], u2, v2);
+            dmma884(acc[8][0], acc[8][1], u2, v3);
+            dmma884(acc[9][0], acc[9][1], u3, v3);
             dmma884(acc[10][0], acc[10][1], llg * r89.x, bf);
             dmma884(acc[11][0], acc[11][1], llg * r89.y, bf);
-            const double c12 = t12 ? (t12l ? s23.y : s23.x) * s23.y : 0.0;          // LL_8 = L_2 L_3, LL_9 = L_3 L_3
-            dmma884(acc[12][0], acc[12][1], c12 * (t12r ? r89.y : r89.x), bf);
+            // tile 12: LL_8 = L_2 L_3, LL_9 = L_3 L_3  ->  A = L_2|3 RR_8|9,  B = B_g L_3
+            const double c12 = t12 ? (t12l ? s23.y : s23.x) : 0.0;
+            dmma884(acc[12][0], acc[12][1], c12 * (t12r ? r89.y : r89.x), v3);
             dmma884(acc[13][0], acc[13][1], (hi ? s01.y : s01.x) * rb, fy);
             dmma884(acc[14][0], acc[14][1], (hi ? s23.y : s23.x) * rb, fy);
         }

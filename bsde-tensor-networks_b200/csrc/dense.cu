@@ -522,72 +522,18 @@ __device__ void lu_solve(SolveScratch& S, int n, double* xout) {
         }                                                                                            \
     } while (0)
 
-__global__ void __launch_bounds__(kDenseThreads)
-k_micro_solve(MicroSolveArgs a) {
-    extern __shared__ double sm[];
-    long long t_phase = a.clk ? clock64() : 0;
-    const int n = a.rl * a.p * a.rr;
-    const int ld = n + 3;
-    SolveScratch S;
-    S.A = sm;                                   // (n+2) x (n+3): augmented normal equations / Jacobi G / QR work matrix
-    S.G = sm;
-    S.V = sm + (size_t)(n + 2) * (n + 3);       // n^2     : Jacobi right vectors
-    S.x = S.V + (size_t)n * n;                  // n
-    S.sc = S.x + n;                             // n
-    S.bvec = S.sc + n;                          // n
-    S.red = S.bvec + n;                         // n       : Jacobi solution scratch
-    double* W = S.red + n;                      // kMaxR*kMaxP*kMaxR : neighbour-core product
-    double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
-    double* tau = qrR + kMaxR * kMaxR;          // kMaxR
-    double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
-    double* stage_buf = vbuf + kMaxR * kMaxP + 16;   // a.n_slots : the assembly kernel's summed slots
-    __shared__ int s_path, s_rank, s_ok;
-    __shared__ double s_red[4];
-
-    expand_normal_equations(a, S.A, ld, S.bvec, stage_buf);
-    __syncthreads();
-    BSDE_PHASE(0);
-    if (a.dbg_A) {
-        for (int e = threadIdx.x; e < n * n; e += blockDim.x) a.dbg_A[e] = S.A[(e / n) * ld + (e % n)];
-        for (int e = threadIdx.x; e < n; e += blockDim.x) a.dbg_A[n * n + e] = S.bvec[e];
-    }
-    __syncthreads();
-    if (a.solver == SOLVER_LSTSQ) {
-        {
-            const bool ok = cholesky_solve(S, n, S.x, s_red);
-            if (threadIdx.x == 0) { s_ok = ok ? 1 : 0; s_path = ok ? 0 : 1; s_rank = n; }
-        }
-        __syncthreads();
-        if (!s_ok) {
-            // rebuild A (column-major == row-major, A is symmetric) with ld = n for the Jacobi path
-            expand_normal_equations(a, S.G, n, S.bvec, stage_buf);
-            __syncthreads();
-            double* xtmp = S.red;
-            const int rank = jacobi_lstsq(S, n, S.bvec, xtmp);
-            for (int i = threadIdx.x; i < n; i += blockDim.x) S.x[i] = xtmp[i];
-            if (threadIdx.x == 0) s_rank = rank;
-            __syncthreads();
-        }
-    } else {
-        lu_solve(S, n, S.x);
-        if (threadIdx.x == 0) { s_path = 2; s_rank = n; }
-    }
-    __syncthreads();
-    BSDE_PHASE(1);
-    if (threadIdx.x == 0 && a.info) {          // counters: [0] cholesky, [1] jacobi, [2] lu, [3] min numerical rank
-        a.info[s_path] += 1;
-        if (s_rank < a.info[3]) a.info[3] = s_rank;
-    }
-
+// Orthogonalisation step of the sweep (als.py:70-77 / :87-94): QR of the solved core, push of the triangular factor into
+// the neighbouring core.  Mq: work matrix (n doubles), W / qrR / tau / vbuf: scratch as laid out by the kernels.
+__device__ void orthogonalise_and_push(const MicroSolveArgs& a, int n, const double* x, double* Mq, double* W, double* qrR,
+                                       double* tau, double* vbuf, long long& t_phase) {
     // ---- orthogonalisation step of the sweep (als.py:70-77 / :87-94) ----
-    double* Mq = S.A;   // the factorisation storage is free now
     if (a.direction == 0) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) a.core_j[i] = S.x[i];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) a.core_j[i] = x[i];
         return;
     }
     if (a.direction > 0) {
         const int mrows = a.rl * a.p, k = a.rr;            // left_unfold(X): (rl*p) x rr, row-major == x itself
-        for (int i = threadIdx.x; i < n; i += blockDim.x) Mq[i] = S.x[i];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) Mq[i] = x[i];
         __syncthreads();
         if (threadIdx.x < 32) {
             if (mrows <= 64 && k <= 4) warp_householder_qr_regs<4>(Mq, mrows, k, k, qrR);
@@ -611,7 +557,7 @@ k_micro_solve(MicroSolveArgs a) {
         const int mrows = a.p * a.rr, k = a.rl;            // right_unfold(X)^T: (p*rr) x rl
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
             const int r = e / k, c = e % k;                 // Mq[r][c] = X[c][r]
-            Mq[e] = S.x[c * mrows + r];
+            Mq[e] = x[c * mrows + r];
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -637,6 +583,377 @@ k_micro_solve(MicroSolveArgs a) {
         for (int e = threadIdx.x; e < rows * k; e += blockDim.x) a.core_nb[e] = W[e];
     }
     BSDE_PHASE(3);
+}
+
+// =====================================================================================================================
+// Fast path of the ALS micro-step for n <= 64 unknowns: k_micro_solve_fast (256 threads, matrix in registers)
+// =====================================================================================================================
+// k_micro_solve runs 1024 threads (the Jacobi fallback wants one warp per column pair), i.e. 64 registers per thread, and
+// its Cholesky moves every trailing entry through the shared memory of the one SM once per column pair: ~1400 cycles per
+// pair at n = 64 although the dependent FP64 chain is short (DFMA latency is 8 cycles, bench/micro/fp64_latency.cu).
+// Here the augmented lower triangle (rows n, n+1 = right-hand sides b and the +-1 probe, see cholesky_solve) lives in
+// REGISTERS for the whole factorisation: thread (ty, tx) of a 16 x 16 grid owns the 2 x 2 blocks (R, C), R = ty + 16 a,
+// C = tx + 16 b.  Per column pair t only the two pivot columns are published through (ping-pong) shared memory and the
+// owner of the diagonal block publishes the reciprocal pivots; one block barrier per pair.  The factor is written out as
+// the UNIT lower-triangular L~ of A = L~ D L~^T (row-major, Lr[i][k] = L_ik / L_kk), the right-hand-side rows as
+// D^-1 L~^-1 rhs, so the back substitution is one shuffle + one FMA per step on register-resident accumulators.
+// Same acceptance test as cholesky_solve; when it fails (or a pivot is not positive) the kernel only sets *fast_flag = 1
+// and k_micro_solve, launched right behind it, redoes the micro-step on its SVD path.  *fast_flag = 0: done.
+constexpr int kFastThreads = 256;
+constexpr int kFastColPitch = 72;
+
+struct FastTile {
+    // Shared-memory byte addresses of this thread's rows / columns in the published pivot columns (parity 0;
+    // + kFastParityBytes for parity 1) and in the factor, made opaque to the compiler (it otherwise rebuilds them from
+    // threadIdx in every iteration: 450 instructions per column pair for 74 FP64 operations) and used through explicit
+    // ld.shared / st.shared (generic accesses cost a far longer round trip).  Slots without a block point at dummies.
+    unsigned crow[3];               // &cu[2 R]      (cw = + kFastColPitch doubles)
+    unsigned ccol[2];               // &cu[2 C]
+    unsigned lrow[3][2];            // row 2 R + r of Lr
+    unsigned piv;                   // pivbuf
+    int tx, ty;
+};
+constexpr unsigned kFastParityBytes = 2 * kFastColPitch * 8;     // between the two ping-pong column buffers
+constexpr unsigned kFastCwBytes = kFastColPitch * 8;            // from column 2t to column 2t + 1
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ double2 lds2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts2(unsigned addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts1(unsigned addr, double x) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory");
+}
+
+// Publishes column pair t of this thread's row blocks (column block TB) into the ping-pong buffers of parity t & 1;
+// the owner of the diagonal block adds the reciprocal pivots.  Called by the threads with tx == t % 16 only.
+template <int TB>
+__device__ __forceinline__ void fast_publish(const FastTile& ft, const double (&e)[3][2][2][2], int t) {
+    const unsigned par = (t & 1) * kFastParityBytes;
+#pragma unroll
+    for (int ai = TB; ai < 3; ai++) {             // row block 0 is finished when TB = 1
+        sts2(ft.crow[ai] + par, e[ai][TB][0][0], e[ai][TB][1][0]);
+        sts2(ft.crow[ai] + par + kFastCwBytes, e[ai][TB][0][1], e[ai][TB][1][1]);
+    }
+    if (ft.ty == (t & 15)) {
+        const unsigned pv = ft.piv + (t & 1) * 32;
+        const double p0 = e[TB][TB][0][0], a10 = e[TB][TB][1][0], w11 = e[TB][TB][1][1];
+        const double i0 = fast_rcp(p0);
+        const double l10 = a10 * i0;
+        const double p1 = fma(-l10, a10, w11);
+        const double i1 = fast_rcp(p1);
+        sts2(pv, i0, a10);
+        sts2(pv + 16, i1, (p0 > 0.0 && p1 > 0.0) ? 1.0 : 0.0);
+        sts1(ft.lrow[TB][1] + 16 * t, l10);
+    }
+}
+
+// One column pair t of k_micro_solve_fast; its columns and pivots were published before the barrier at the top.
+// TB = t / 16 = the column block the pair lives in, TBN = that of pair t + 1 (compile time, so that the register tile is
+// never indexed dynamically).  The threads that own column pair t + 1 update those blocks FIRST and publish them (the
+// owner of the next diagonal block also its reciprocal pivots), so that the dependent chain from one pivot to the next
+// — update, two reciprocals, shared-memory round trip — overlaps with the bulk of the trailing update.
+// Finished rows / columns and the blocks above the diagonal are updated like everything else — their registers are dead
+// and the factor entries they write lie above the diagonal, which the back substitution never reads — so the body is
+// branch-free apart from the publishing threads.  Returns true when a pivot is not positive (uniform over the CTA).
+template <int TB, int TBN>
+__device__ __forceinline__ bool fast_pair_step(const FastTile& ft, double (&e)[3][2][2][2], int t, bool last) {
+    const unsigned par = (t & 1) * kFastParityBytes;
+    const unsigned pv = ft.piv + (t & 1) * 32;
+    const int t15 = t & 15;
+    constexpr int A0 = TB, B0 = TB;              // row block 0 / column block 0 are finished when TB = 1
+    __syncthreads();
+    const double2 pa = lds2(pv), pb = lds2(pv + 16);
+    if (pb.y == 0.0) return true;
+    const double i0 = pa.x, a10 = pa.y, i1 = pb.x;
+    double uj[2][2], vj[2][2], li0[3][2], li1[3][2];
+#pragma unroll
+    for (int bi = B0; bi < 2; bi++) {
+        const double2 u = lds2(ft.ccol[bi] + par), w = lds2(ft.ccol[bi] + par + kFastCwBytes);
+        uj[bi][0] = u.x; uj[bi][1] = u.y;
+        vj[bi][0] = fma(-(u.x * i0), a10, w.x);
+        vj[bi][1] = fma(-(u.y * i0), a10, w.y);
+    }
+#pragma unroll
+    for (int ai = A0; ai < 3; ai++) {
+        const double2 u = lds2(ft.crow[ai] + par), w = lds2(ft.crow[ai] + par + kFastCwBytes);
+        li0[ai][0] = u.x * i0; li0[ai][1] = u.y * i0;
+        li1[ai][0] = fma(-li0[ai][0], a10, w.x) * i1;
+        li1[ai][1] = fma(-li0[ai][1], a10, w.y) * i1;
+    }
+    // the next pivot columns first
+    const bool next_owner = !last && ft.tx == ((t + 1) & 15);
+    if (next_owner) {
+#pragma unroll
+        for (int ai = TBN; ai < 3; ai++)
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+                    e[ai][TBN][r][c] = fma(-li1[ai][r], vj[TBN][c], fma(-li0[ai][r], uj[TBN][c], e[ai][TBN][r][c]));
+        fast_publish<TBN>(ft, e, t + 1);
+    }
+    if (ft.tx == t15) {
+#pragma unroll
+        for (int ai = A0; ai < 3; ai++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) sts2(ft.lrow[ai][r] + 16 * t, li0[ai][r], li1[ai][r]);
+    }
+#pragma unroll
+    for (int ai = A0; ai < 3; ai++)
+#pragma unroll
+        for (int bi = B0; bi < 2; bi++) {
+            if (ai == 0 && bi == 1) continue;    // row pair < 16 <= column pair: above the diagonal for every thread
+            if (bi == TBN && ai >= TBN && next_owner) continue;      // done above
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+                    e[ai][bi][r][c] = fma(-li1[ai][r], vj[bi][c], fma(-li0[ai][r], uj[bi][c], e[ai][bi][r][c]));
+        }
+    return false;
+}
+
+__global__ void __launch_bounds__(kFastThreads, 1)
+k_micro_solve_fast(MicroSolveArgs a) {
+    extern __shared__ double sm[];
+    long long t_phase = a.clk ? clock64() : 0;
+    const int n = a.rl * a.p * a.rr;
+    const int np = (n + 1) & ~1;                // odd n: padded with an identity row / column
+    const int NP = np >> 1;                     // column pairs; row pair NP = the two right-hand-side rows
+    const int ld = np + 4;                      // even: the factor is written in 16-byte pairs
+    double* colbuf = sm;                        // [2 parities][2 columns][kFastColPitch]   (16-byte aligned)
+    double* pivbuf = colbuf + 4 * kFastColPitch;   // [2 parities][4]
+    double* Lr = pivbuf + 8;                    // (np + 3) x ld: factor rows, two right-hand-side rows, one dummy row
+    double* sc = Lr + (size_t)(np + 3) * ld;    // np
+    double* xs = sc + np;                       // np
+    double* W = xs + np;                        // kMaxR*kMaxP*kMaxR
+    double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
+    double* tau = qrR + kMaxR * kMaxR;          // kMaxR
+    double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
+    double* stage = vbuf + kMaxR * kMaxP + 16;  // a.n_slots
+    __shared__ double s_red[4];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+
+    // ---- the map entries of this thread's blocks (global loads issued before the moments are staged) ----
+    const uint16_t* map = a.expand_map;
+    int Rw[3], Cw[2];
+    bool rowok[3], colok[2];
+#pragma unroll
+    for (int ai = 0; ai < 3; ai++) { Rw[ai] = ty + 16 * ai; rowok[ai] = Rw[ai] <= NP; }
+#pragma unroll
+    for (int bi = 0; bi < 2; bi++) { Cw[bi] = tx + 16 * bi; colok[bi] = Cw[bi] < NP; }
+    int midx[3][2][2][2];
+#pragma unroll
+    for (int ai = 0; ai < 3; ai++)
+#pragma unroll
+        for (int bi = 0; bi < 2; bi++)
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int j = 2 * Cw[bi] + c;
+                    int m = -1;                                     // -1: zero, -2: one (padding diagonal), -3: probe
+                    if (rowok[ai] && colok[bi] && j < n) {
+                        if (Rw[ai] < NP) {
+                            const int i = 2 * Rw[ai] + r;
+                            if (i < n) { if (j <= i) m = map[i * n + j]; }
+                        } else {
+                            m = r == 0 ? (int)map[n * n + j] : -3;
+                        }
+                    } else if (rowok[ai] && colok[bi] && Rw[ai] < NP && 2 * Rw[ai] + r == j) {
+                        m = -2;
+                    }
+                    midx[ai][bi][r][c] = m;
+                }
+    const int dmap = tid < n ? (int)map[tid * n + tid] : -1;
+    for (int e = tid; e < a.n_slots; e += kFastThreads) stage[e] = a.moments[e];
+    __syncthreads();
+    // ---- equilibration, trace, positivity of the diagonal ----
+    if (tid < np) {
+        const double d = tid < n ? stage[dmap] : 1.0;
+        sc[tid] = rsqrt(d);
+        xs[tid] = d;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double tr = 0.0;
+        int bad = 0;
+        for (int i = tid; i < n; i += 32) {
+            const double d = xs[i];
+            if (!(d > 0.0) || !isfinite(d)) bad = 1;
+            tr += d;
+        }
+        tr = warp_sum(tr);
+        bad = __any_sync(0xffffffffu, bad);
+        if (tid == 0) { s_red[0] = tr; s_red[1] = bad ? 1.0 : 0.0; }
+    }
+    double e[3][2][2][2];
+#pragma unroll
+    for (int ai = 0; ai < 3; ai++)
+#pragma unroll
+        for (int bi = 0; bi < 2; bi++)
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int m = midx[ai][bi][r][c];
+                    const int j = min(2 * Cw[bi] + c, np - 1);
+                    double v = 0.0;
+                    if (m >= 0) v = stage[m];
+                    else if (m == -2) v = 1.0;
+                    else if (m == -3) v = (((unsigned)j * 2654435761u) >> 7) & 1u ? 1.0 : -1.0;
+                    v *= sc[j];
+                    if (Rw[ai] < NP) v *= sc[min(2 * Rw[ai] + r, np - 1)];
+                    e[ai][bi][r][c] = v;
+                }
+    __syncthreads();
+    if (s_red[1] != 0.0) { if (tid == 0) *a.fast_flag = 1; return; }
+    BSDE_PHASE(0);
+    long long t_sub = t_phase;
+    if (a.stop_after == 1) return;
+
+    // ---- factorisation: column pairs 0..15 (column block 0), then 16.. (column block 1: row block 0 and column
+    // block 0 are finished by then, so that half touches a third of the registers) ----
+    FastTile ft;
+    // dummy targets of slots without a block: entries 68.. of the published columns, row np + 2 of the factor
+#pragma unroll
+    for (int ai = 0; ai < 3; ai++) {
+        ft.crow[ai] = smem_addr(colbuf + (rowok[ai] ? 2 * Rw[ai] : 68));
+#pragma unroll
+        for (int r = 0; r < 2; r++) ft.lrow[ai][r] = smem_addr(Lr + (size_t)(rowok[ai] ? 2 * Rw[ai] + r : np + 2) * ld);
+    }
+#pragma unroll
+    for (int bi = 0; bi < 2; bi++) ft.ccol[bi] = smem_addr(colbuf + (colok[bi] ? 2 * Cw[bi] : 70));
+    ft.piv = smem_addr(pivbuf);
+    ft.tx = tx; ft.ty = ty;
+    bool failed = false;
+    if (tx == 0) fast_publish<0>(ft, e, 0);
+    for (int t = 0; t < NP && t < 15 && !failed; t++) failed = fast_pair_step<0, 0>(ft, e, t, t == NP - 1);
+    if (NP > 15 && !failed) failed = fast_pair_step<0, 1>(ft, e, 15, NP == 16);
+    for (int t = 16; t < NP && !failed; t++) failed = fast_pair_step<1, 1>(ft, e, t, t == NP - 1);
+    if (failed) { if (tid == 0) *a.fast_flag = 1; return; }      // uniform
+    if (a.stop_after == 2) return;
+    __syncthreads();
+    if (a.clk && tid == 0) { const long long now = clock64(); atomicAdd((unsigned long long*)(a.clk + 5), (unsigned long long)(now - t_sub)); t_sub = now; }
+
+    // ---- back substitution L~^T x = D^-1 L~^-1 rhs: warp 0 -> b, warp 1 -> probe; lane l carries rows l and l + 32 ----
+    if (tid < 64) {
+        const int lane = tid & 31;
+        const double* zrow = Lr + (np + (tid >> 5)) * ld;
+        double acc0 = lane < np ? zrow[lane] : 0.0, acc1 = lane + 32 < np ? zrow[lane + 32] : 0.0;
+        double r0 = 0.0, r1 = 0.0;                // row kk of L~ (columns lane, lane + 32), fetched one step ahead
+        {
+            const double* row = Lr + (np - 1) * ld;
+            r0 = lane < np - 1 ? row[lane] : 0.0;
+            r1 = lane + 32 < np - 1 ? row[lane + 32] : 0.0;
+        }
+        for (int kk = np - 1; kk >= 0; kk--) {
+            const double c0 = r0, c1 = r1;
+            if (kk > 0) {
+                const double* row = Lr + (kk - 1) * ld;
+                r0 = lane < kk - 1 ? row[lane] : 0.0;
+                r1 = lane + 32 < kk - 1 ? row[lane + 32] : 0.0;
+            }
+            const double xk = __shfl_sync(0xffffffffu, (kk & 32) ? acc1 : acc0, kk & 31);
+            acc0 = fma(-c0, xk, acc0);            // c = 0 for columns >= kk: finished rows keep their value
+            acc1 = fma(-c1, xk, acc1);
+        }
+        const double v0 = lane < n ? acc0 * sc[lane] : 0.0, v1 = lane + 32 < n ? acc1 * sc[lane + 32] : 0.0;
+        if (tid < 32) {
+            if (lane < n) xs[lane] = v0;
+            if (lane + 32 < n) xs[lane + 32] = v1;
+        } else {
+            const double zz = warp_sum(fma(v0, v0, v1 * v1));
+            if (lane == 0) s_red[2] = zz;
+        }
+    }
+    __syncthreads();
+    if (a.clk && tid == 0) { const long long now = clock64(); atomicAdd((unsigned long long*)(a.clk + 6), (unsigned long long)(now - t_sub)); }
+    {
+        const double zz = s_red[2];
+        const bool ok = isfinite(zz) && zz > 0.0 && sqrt((double)n / zz) / s_red[0] > kGateSafety * DBL_EPSILON * (double)n;
+        if (!ok) { if (tid == 0) *a.fast_flag = 1; return; }
+    }
+    BSDE_PHASE(1);
+    if (a.stop_after == 3) return;
+    if (tid == 0) {
+        *a.fast_flag = 0;
+        if (a.info) { a.info[0] += 1; if (n < a.info[3]) a.info[3] = n; }
+    }
+    orthogonalise_and_push(a, n, xs, Lr /* the factor is not needed any more */, W, qrR, tau, vbuf, t_phase);
+}
+
+__global__ void __launch_bounds__(kDenseThreads)
+k_micro_solve(MicroSolveArgs a) {
+    extern __shared__ double sm[];
+    long long t_phase = a.clk ? clock64() : 0;
+    const int n = a.rl * a.p * a.rr;
+    const int ld = n + 3;
+    SolveScratch S;
+    S.A = sm;                                   // (n+2) x (n+3): augmented normal equations / Jacobi G / QR work matrix
+    S.G = sm;
+    S.V = sm + (size_t)(n + 2) * (n + 3);       // n^2     : Jacobi right vectors
+    S.x = S.V + (size_t)n * n;                  // n
+    S.sc = S.x + n;                             // n
+    S.bvec = S.sc + n;                          // n
+    S.red = S.bvec + n;                         // n       : Jacobi solution scratch
+    double* W = S.red + n;                      // kMaxR*kMaxP*kMaxR : neighbour-core product
+    double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
+    double* tau = qrR + kMaxR * kMaxR;          // kMaxR
+    double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
+    double* stage_buf = vbuf + kMaxR * kMaxP + 16;   // a.n_slots : the assembly kernel's summed slots
+    __shared__ int s_path, s_rank, s_ok;
+    __shared__ double s_red[4];
+
+    // behind k_micro_solve_fast: nothing to do unless the fast path gave up (then straight to the SVD path)
+    const bool after_fast = a.fast_flag != nullptr;
+    if (after_fast && *a.fast_flag == 0) return;
+
+    expand_normal_equations(a, S.A, ld, S.bvec, stage_buf);
+    __syncthreads();
+    BSDE_PHASE(0);
+    if (a.dbg_A) {
+        for (int e = threadIdx.x; e < n * n; e += blockDim.x) a.dbg_A[e] = S.A[(e / n) * ld + (e % n)];
+        for (int e = threadIdx.x; e < n; e += blockDim.x) a.dbg_A[n * n + e] = S.bvec[e];
+    }
+    __syncthreads();
+    if (a.solver == SOLVER_LSTSQ) {
+        {
+            const bool ok = after_fast ? false : cholesky_solve(S, n, S.x, s_red);
+            if (threadIdx.x == 0) { s_ok = ok ? 1 : 0; s_path = ok ? 0 : 1; s_rank = n; }
+        }
+        __syncthreads();
+        if (!s_ok) {
+            // rebuild A (column-major == row-major, A is symmetric) with ld = n for the Jacobi path
+            expand_normal_equations(a, S.G, n, S.bvec, stage_buf);
+            __syncthreads();
+            double* xtmp = S.red;
+            const int rank = jacobi_lstsq(S, n, S.bvec, xtmp);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) S.x[i] = xtmp[i];
+            if (threadIdx.x == 0) s_rank = rank;
+            __syncthreads();
+        }
+    } else {
+        lu_solve(S, n, S.x);
+        if (threadIdx.x == 0) { s_path = 2; s_rank = n; }
+    }
+    __syncthreads();
+    BSDE_PHASE(1);
+    if (threadIdx.x == 0 && a.info) {          // counters: [0] cholesky, [1] jacobi, [2] lu, [3] min numerical rank
+        a.info[s_path] += 1;
+        if (s_rank < a.info[3]) a.info[3] = s_rank;
+    }
+
+    orthogonalise_and_push(a, n, S.x, S.A /* the factorisation storage is free now */, W, qrR, tau, vbuf, t_phase);
 }
 
 // Whole-train orthonormalisation by successive QRs (tensor_train.py:34-87), one CTA, cores in global memory.
@@ -705,7 +1022,7 @@ k_orthonormalize(OrthoArgs a) {
 
 }  // namespace
 
-int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st) {
+int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_launches) {
     const int n = a.rl * a.p * a.rr;
     if (n > kMaxN) return fail_msg(2, "micro_solve: n = %d unknowns exceeds the in-CTA solver limit %d", n, kMaxN);
     if (a.direction > 0 && a.rl * a.p < a.rr) return fail_msg(2, "micro_solve: left QR needs r_j*p >= r_{j+1} (%d*%d < %d)", a.rl, a.p, a.rr);
@@ -717,11 +1034,27 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         BSDE_CUDA_OK(cudaFuncSetAttribute(k_micro_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        BSDE_CUDA_OK(cudaFuncSetAttribute(k_micro_solve_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
     if (bytes > 220 * 1024) return fail_msg(2, "micro_solve: n = %d needs %zu B of shared memory", n, bytes);
-    k_micro_solve<<<1, kDenseThreads, bytes, st>>>(a);
+    MicroSolveArgs b = a;
+    // plain ALS micro-step of at most 64 unknowns: the register-resident kernel first, k_micro_solve behind it as the
+    // fallback that returns at once unless the fast path gave up
+    const bool fast = a.fast_flag && a.solver == SOLVER_LSTSQ && n <= 64 && !a.reg_diag && !a.eta_ptr && a.ridge == 0.0 &&
+                      !a.A_direct && !a.dbg_A && a.n_slots > 0;
+    if (fast) {
+        const int np = (n + 1) & ~1;
+        const size_t fd = (size_t)(np + 3) * (np + 4) + 2 * (size_t)np + 4 * kFastColPitch + 8 + kMaxR * kMaxP * kMaxR +
+                          kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16 + (size_t)a.n_slots + 16;
+        k_micro_solve_fast<<<1, kFastThreads, fd * sizeof(double), st>>>(a);
+        BSDE_CUDA_OK(cudaGetLastError());
+    } else {
+        b.fast_flag = nullptr;
+    }
+    k_micro_solve<<<1, kDenseThreads, bytes, st>>>(b);
     BSDE_CUDA_OK(cudaGetLastError());
+    if (extra_launches) *extra_launches = fast ? 1 : 0;
     return 0;
 }
 

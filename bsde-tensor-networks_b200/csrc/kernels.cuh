@@ -100,10 +100,13 @@ struct MicroSolveArgs {
     long long* clk = nullptr;           // optional: 4 phase-cycle accumulators (expand, solve, QR, push)
     double* dbg_A;           // optional n*n + n (A | b) dump for parity tests
     int* info;               // accumulated: [0] cholesky solves, [1] jacobi-svd solves, [2] lu solves, [3] min numerical rank
+    int stop_after = 0;                 // measurement only: k_micro_solve_fast returns after phase 1 (load), 2 (factor), 3 (solve)
+    int* fast_flag = nullptr;           // device int: enables k_micro_solve_fast (written 0 = done, 1 = fallback needed)
     const double* A_direct = nullptr;   // explicit n x n system (then rl = n, p = rr = 1 and moments is unused)
     const double* b_direct = nullptr;
 };
-int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st);
+// *extra_launches: kernels launched in front of k_micro_solve (the fast kernel, see dense.cu)
+int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_launches = nullptr);
 int launch_orthonormalize_right(double* cores, const int64_t* core_off_host, const int* ranks_host, int p, int d,
                                 int start, int stop, cudaStream_t st);
 int launch_orthonormalize_left(double* cores, const int64_t* core_off_host, const int* ranks_host, int p, int d,

@@ -22,5 +22,8 @@ ranks = np.array([1] + [r] * (d - 1) + [1], dtype=np.int32)
 rng = np.random.RandomState(0)
 cores = np.concatenate([(rng.rand(ranks[i] * p * ranks[i + 1]) - 0.5) * 2 for i in range(d)])
 be.set_option("use_graph", 0)
+for kv in sys.argv[3:]:          # further library options, name=value
+    name, _, val = kv.partition("=")
+    be.set_option(name, int(val))
 info = be.fit_als(DeviceInputs(BASIS_POLY, p, xT), y, sweeps, ranks, 0, cores)
 print("fit done", info.tolist(), "launches", be.launch_count())

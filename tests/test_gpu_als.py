@@ -175,6 +175,38 @@ def test_fused_interface_update_is_bit_identical(backend):
         assert out[(1, 1)][1] < out[(0, 1)][1]
 
 
+def test_fast_solve_kernel_matches_the_general_one(backend):
+    """k_micro_solve_fast (register-resident Cholesky, n <= 64) against k_micro_solve alone on the same fits: even and odd
+    numbers of unknowns, ragged ranks, and agreement with the numpy oracle."""
+    import oracle.tt_oracle as O
+    from bsde_solver._backend import DeviceInputs
+    from bsde_solver._lib import BASIS_POLY
+
+    rng = np.random.RandomState(21)
+    for d, p, ranks, N in ((4, 3, [1, 3, 3, 3, 1], 3000), (6, 4, [1, 4, 4, 4, 4, 4, 1], 20000), (5, 3, [1, 2, 3, 3, 2, 1], 1531),
+                           (3, 5, [1, 3, 3, 1], 2500), (4, 4, [1, 4, 4, 2, 1], 4097)):
+        x = rng.rand(N, d) * 2 - 1
+        y = np.cos(x.sum(axis=1)) + 0.3 * x[:, 0] * x[:, -1]
+        init = [rng.rand(ranks[i], p, ranks[i + 1]) * 2 - 1 for i in range(d)]
+        phis = [O.poly_eval(x[:, i], p) for i in range(d)]
+        ref = O.tt_eval(O.als(phis, y, n_iter=5, cores=[c.copy() for c in init], randomize=False), phis)
+        inp = DeviceInputs(BASIS_POLY, p, backend.to_device(np.ascontiguousarray(x.T)))
+        yd = backend.to_device(y)
+        fits, infos = {}, {}
+        try:
+            for fast in (0, 1):
+                backend.set_option("fast_solve", fast)
+                got = flat(init)
+                infos[fast] = backend.fit_als(inp, yd, 5, np.array(ranks, dtype=np.int32), 0, got)
+                fits[fast] = backend.tt_eval(inp, ranks, got).cpu().numpy()
+        finally:
+            backend.set_option("fast_solve", 1)
+        assert list(infos[0]) == list(infos[1]), (ranks, infos)          # same solver path taken by every micro-step
+        assert infos[1][0] > 0
+        assert rel(fits[1], fits[0]) < 1e-10, (ranks, rel(fits[1], fits[0]))
+        assert rel(fits[1], ref) < 1e-9, (ranks, rel(fits[1], ref))
+
+
 def test_step0_fit_returns_mean(backend):
     """at time step 0 all samples coincide, A has rank 1, lstsq's minimum-norm solution fits mean(y)."""
     from bsde_solver._backend import DeviceInputs
