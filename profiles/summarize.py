@@ -1,6 +1,7 @@
 """Turn ncu outputs into the small text summaries committed under profiles/.
 
     python profiles/summarize.py rep  gpurun_out/prof.ncu-rep   > profiles/<name>.txt     (needs ncu on PATH, no GPU)
+    python profiles/summarize.py rep  gpurun_out/asm_raw.csv    > profiles/<name>.txt     (raw page exported by profiles/capture.sh)
     python profiles/summarize.py list gpurun_out/launches.csv   > profiles/<name>.txt
 """
 import collections
@@ -17,11 +18,15 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__sass_inst_executed_op_local_ld.sum", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg",
-        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum"]
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
+        "smsp__warps_eligible.avg.per_cycle_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def rep(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):          # already reduced on the GPU box (profiles/capture.sh)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     name_col = hdr.index("Kernel Name")
