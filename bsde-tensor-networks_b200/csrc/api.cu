@@ -99,6 +99,7 @@ struct bsde_ctx {
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
     int64_t solve_stop = 0;       // measurement only (MicroSolveArgs::stop_after)
+    int64_t gate_tier2 = 1;       // option: second-tier acceptance test in k_micro_solve_fast (MicroSolveArgs::tier2)
     int64_t svd_onesided = 0;     // A/B measurement: one-sided Jacobi SVD for symmetric systems too (MicroSolveArgs::force_onesided)
     int64_t fast_solve = 1;       // option: register-resident fast kernel in front of k_micro_solve (dense.cu)
     int64_t fuse_interface = 1;   // option: ALS forms the trailing interface inside the next assembly kernel (als_sweep)
@@ -388,6 +389,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     if (c->fast_solve && c->scalars.p) a.fast_flag = c->scalars.as<int>() + 24;
     a.stop_after = (int)c->solve_stop;
     a.force_onesided = (int)c->svd_onesided;
+    a.tier2 = (int)c->gate_tier2;
     int extra = 0;
     BSDE_TRY(launch_micro_solve(a, c->stream, &extra));
     c->launches += 1 + extra;
@@ -742,6 +744,7 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     if (name && !strcmp(name, "fast_solve")) { c->fast_solve = value; return 0; }
     if (name && !strcmp(name, "solve_stop")) { c->solve_stop = value; return 0; }
     if (name && !strcmp(name, "svd_onesided")) { c->svd_onesided = value; return 0; }
+    if (name && !strcmp(name, "gate_tier2")) { c->gate_tier2 = value; return 0; }
     if (name && !strcmp(name, "asm_generic")) {
         c->asm_generic = value;
         for (auto& kv : c->plans) asm_plan_free(kv.second);

@@ -100,6 +100,7 @@ struct MicroSolveArgs {
     long long* clk = nullptr;           // optional: 4 phase-cycle accumulators (expand, solve, QR, push)
     double* dbg_A;           // optional n*n + n (A | b) dump for parity tests
     int* info;               // accumulated: [0] cholesky solves, [1] jacobi-svd solves, [2] lu solves, [3] min numerical rank
+    int tier2 = 1;                      // second-tier acceptance test of k_micro_solve_fast (option "gate_tier2")
     int force_onesided = 0;             // A/B measurement: symmetric systems also take the one-sided Jacobi SVD (option "svd_onesided")
     int stop_after = 0;                 // measurement only: k_micro_solve_fast returns after phase 1 (load), 2 (factor), 3 (solve)
     int* fast_flag = nullptr;           // device int: enables k_micro_solve_fast (written 0 = done, 1 = fallback needed)
