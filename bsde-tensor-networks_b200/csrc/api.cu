@@ -99,6 +99,7 @@ struct bsde_ctx {
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
     int64_t solve_stop = 0;       // measurement only (MicroSolveArgs::stop_after)
+    int64_t red_groups = 3;       // option: row groups of the moment reduction on a single GPU (1 = one level; measured best: 3)
     int64_t gate_tier2 = 1;       // option: second-tier acceptance test in k_micro_solve_fast (MicroSolveArgs::tier2)
     int64_t svd_onesided = 0;     // A/B measurement: one-sided Jacobi SVD for symmetric systems too (MicroSolveArgs::force_onesided)
     int64_t fast_solve = 1;       // option: register-resident fast kernel in front of k_micro_solve (dense.cu)
@@ -348,7 +349,10 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     const AsmPlan* P;
     BSDE_TRY(get_plan(c, rl, T.p, rr, m.mono, m.in->N, &P));
     BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
-    BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride));
+    BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride * kRedGroups));
+    // single GPU: the partial rows are summed in kRedGroups groups, added up by the solve kernel; sharded: one group (the
+    // all-reduce, fused or NCCL, works on the complete sums)
+    const int groups = (c->world > 1 || P->grid_x < 8 * kRedGroups) ? 1 : (int)c->red_groups;
     if (fi && fi->side && !asm_fuse_supported(*P, *m.in, *fi)) {      // this shape cannot fuse: separate interface kernel
         cudaEvent_t i0 = prof_mark(c);
         if (fi->side == 1) BSDE_TRY(launch_interface_left(*m.in, fi->j, fi->core, fi->r_in, rl, fi->in, fi->out, c->stream));
@@ -359,7 +363,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     }
     cudaEvent_t e0 = prof_mark(c), e1 = prof_take(c);
     BSDE_TRY(launch_assembly(*P, *m.in, j, j == 0 ? nullptr : m.B->at(j), j == T.d - 1 ? nullptr : m.B->at(j + 1), m.y,
-                             c->partial.as<double>(), c->moments.as<double>(), c->stream, e1, c->px_on ? &c->px : nullptr, fi));
+                             c->partial.as<double>(), c->moments.as<double>(), c->stream, e1, c->px_on ? &c->px : nullptr, fi, groups));
     c->launches += 2;
     cudaEvent_t e2 = prof_mark(c);
     prof_span(c, bsde_ctx::P_ASSEMBLY, e0, e1);
@@ -374,6 +378,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     a.moments = c->moments.as<double>();
     a.expand_map = P->d_expand;
     a.n_slots = (int)P->partial_stride;
+    a.moment_rows = groups;
     a.rl = rl; a.p = T.p; a.rr = rr; a.mono = m.mono; a.nLL = P->nLL; a.nRR = P->nRR; a.nB = P->nB;
     a.direction = direction; a.solver = m.solver;
     a.core_j = T.core(j);
@@ -745,6 +750,7 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     if (name && !strcmp(name, "solve_stop")) { c->solve_stop = value; return 0; }
     if (name && !strcmp(name, "svd_onesided")) { c->svd_onesided = value; return 0; }
     if (name && !strcmp(name, "gate_tier2")) { c->gate_tier2 = value; return 0; }
+    if (name && !strcmp(name, "red_groups")) { if (value < 1 || value > kRedGroups) return fail_msg(2, "red_groups outside 1..%d", kRedGroups); c->red_groups = value; return 0; }
     if (name && !strcmp(name, "asm_generic")) {
         c->asm_generic = value;
         for (auto& kv : c->plans) asm_plan_free(kv.second);

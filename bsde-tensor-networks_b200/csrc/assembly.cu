@@ -466,8 +466,13 @@ k_assemble_r4(AsmArgs a) {
     const int64_t nchunks = (a.in.N + 31) / 32;
     const int64_t warps_total = (int64_t)gridDim.x * kAsmWarps;
     RawSample<4, 4> raw;
+#ifndef BSDE_R4_NOPREFETCH
     load_raw<4, 4>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
+#endif
     for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
+#ifdef BSDE_R4_NOPREFETCH
+        load_raw<4, 4>(a, lane, chunk, nchunks, raw);      // 4 CTAs per SM: the other warps cover the DRAM latency
+#endif
         if (a.fuse) fuse_interface<4, 4>(a, score, chunk * 32 + lane, raw);
         {   // ---- phase 1: lane = sample ----
             const double vm = raw.vm, yv = raw.y * vm;
@@ -498,7 +503,9 @@ k_assemble_r4(AsmArgs a) {
             }
             accyy += yv * yv;
         }
+#ifndef BSDE_R4_NOPREFETCH
         load_raw<4, 4>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
+#endif
         __syncwarp();
         // ---- phase 2: 8 k-steps of 4 samples, 15 DMMA each ----
 #pragma unroll
@@ -620,6 +627,16 @@ k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, in
     __shared__ double part[kRedWarps][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
+    // gridDim.y row groups (kRedGroups on a single GPU): group g sums its contiguous share of the partial rows into row g of
+    // `sums`; the solve kernels add the few group rows in order while staging the moments.  One group of 444 rows keeps
+    // only 24 SMs busy for 11 us; six groups finish in a third of that.  Still a fixed summation tree.
+    {
+        const int per = (rows + gridDim.y - 1) / gridDim.y;
+        const int first = blockIdx.y * per;
+        partial += (int64_t)first * stride;
+        sums += (int64_t)blockIdx.y * stride;
+        rows = max(0, min(per, rows - first));
+    }
     double acc[16];
 #pragma unroll
     for (int u = 0; u < 16; u++) acc[u] = 0.0;
@@ -936,7 +953,7 @@ void asm_plan_free(AsmPlan& P) {
 
 int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, const double* R, const double* y,
                     double* partial, double* moments, cudaStream_t st, cudaEvent_t mid, const PeerExchange* px,
-                    const FusedInterface* fi) {
+                    const FusedInterface* fi, int moment_groups) {
     AsmArgs a;
     a.in = in; a.j = j; a.L = L; a.R = R; a.y = y;
     a.fuse = 0; a.fj = 0; a.fr_in = 0; a.fcore = nullptr; a.f_in = nullptr; a.f_out = nullptr; a.core_off = P.core_off;
@@ -962,7 +979,9 @@ int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, 
         if (red_blocks > kXBlocks || red_blocks * 32 > kXSlots) return fail_msg(2, "assembly: %d reduce blocks exceed the peer-exchange buffer", red_blocks);
         ex = *px;
     }
-    k_moment_reduce<<<red_blocks, 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride, (int)P.partial_stride, moments, ex);
+    if (moment_groups < 1 || (ex.world > 1 && moment_groups != 1)) return fail_msg(2, "assembly: %d moment groups", moment_groups);
+    k_moment_reduce<<<dim3(red_blocks, moment_groups), 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride,
+                                                                               (int)P.partial_stride, moments, ex);
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;
 }

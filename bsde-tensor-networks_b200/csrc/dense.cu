@@ -192,6 +192,18 @@ __device__ void warp_householder_qr_regs(double* M, int m, int k, int ld, double
     __syncwarp();
 }
 
+// Slot e of the reduced moments: the sum, in fixed order, of the a.moment_rows (<= kRedGroups) group rows k_moment_reduce
+// left behind.  All loads are issued before the first addition.
+__device__ __forceinline__ double load_moment(const MicroSolveArgs& a, int e) {
+    double t[kRedGroups];
+#pragma unroll
+    for (int g = 0; g < kRedGroups; g++) t[g] = g < a.moment_rows ? a.moments[(size_t)g * a.n_slots + e] : 0.0;
+    double acc = t[0];
+#pragma unroll
+    for (int g = 1; g < kRedGroups; g++) acc += t[g];
+    return acc;
+}
+
 struct SolveScratch {
     double* A;      // (n+1) x (n+1) augmented, row-major, ld = n+1
     double* G;      // n x n column-major (Jacobi)        — aliases A
@@ -212,7 +224,7 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
     // stage the moments in shared memory with coalesced loads (the gather below would otherwise pay one L2 round trip
     // per entry)
     // (a.moments holds the summed partial-row slots of the assembly kernel; a.n_slots of them)
-    for (int e = threadIdx.x; e < a.n_slots; e += blockDim.x) stage[e] = a.moments[e];
+    for (int e = threadIdx.x; e < a.n_slots; e += blockDim.x) stage[e] = load_moment(a, e);
     __syncthreads();
     // a.expand_map[e] (built once per core shape on the host, assembly.cu) = index of the moment that entry e of the
     // row-major A (then of b) is equal to: A[(a,m,b),(a',m',b')] = M1[beta(m,m')][lambda(a,a')][rho(b,b')]
@@ -1007,7 +1019,7 @@ k_micro_solve_fast(MicroSolveArgs a) {
                     midx[ai][bi][r][c] = m;
                 }
     const int dmap = tid < n ? (int)map[tid * n + tid] : -1;
-    for (int e = tid; e < a.n_slots; e += kFastThreads) stage[e] = a.moments[e];
+    for (int e = tid; e < a.n_slots; e += kFastThreads) stage[e] = load_moment(a, e);
     __syncthreads();
     // ---- equilibration, trace, positivity of the diagonal ----
     if (tid < np) {

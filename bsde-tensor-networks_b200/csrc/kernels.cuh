@@ -70,11 +70,12 @@ struct FusedInterface {
 int asm_plan_build(AsmPlan& plan, int rl, int p, int rr, int mono, int64_t N, int sm_count, int force_generic = 0);
 void asm_plan_free(AsmPlan& plan);
 bool asm_fuse_supported(const AsmPlan& plan, const Inputs& in, const FusedInterface& fi);
-// Launches the assembly kernel and the partial reduction; `moments` (n_mom doubles, device) receives
-// [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y].
+// Launches the assembly kernel and the partial reduction; `moments` (moment_groups rows of partial_stride doubles, device)
+// receives [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y] as moment_groups partial sums (MicroSolveArgs::moment_rows adds them).
+constexpr int kRedGroups = 6;
 int launch_assembly(const AsmPlan& plan, const Inputs& in, int j, const double* L, const double* R, const double* y,
                     double* partial, double* moments, cudaStream_t st, cudaEvent_t mid = nullptr,
-                    const PeerExchange* px = nullptr, const FusedInterface* fi = nullptr);
+                    const PeerExchange* px = nullptr, const FusedInterface* fi = nullptr, int moment_groups = 1);
 
 // ---- dense.cu ------------------------------------------------------------------------------------
 enum SolverId : int { SOLVER_LSTSQ = 0, SOLVER_LU = 1, SOLVER_QR = 2, SOLVER_SOLVE = 3 };
@@ -100,6 +101,7 @@ struct MicroSolveArgs {
     long long* clk = nullptr;           // optional: 4 phase-cycle accumulators (expand, solve, QR, push)
     double* dbg_A;           // optional n*n + n (A | b) dump for parity tests
     int* info;               // accumulated: [0] cholesky solves, [1] jacobi-svd solves, [2] lu solves, [3] min numerical rank
+    int moment_rows = 1;                // rows of `moments` to add (fixed order) while staging; row pitch = n_slots
     int tier2 = 1;                      // second-tier acceptance test of k_micro_solve_fast (option "gate_tier2")
     int force_onesided = 0;             // A/B measurement: symmetric systems also take the one-sided Jacobi SVD (option "svd_onesided")
     int stop_after = 0;                 // measurement only: k_micro_solve_fast returns after phase 1 (load), 2 (factor), 3 (solve)
