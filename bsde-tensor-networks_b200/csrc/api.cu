@@ -750,6 +750,7 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     if (name && !strcmp(name, "solve_stop")) { c->solve_stop = value; return 0; }
     if (name && !strcmp(name, "svd_onesided")) { c->svd_onesided = value; return 0; }
     if (name && !strcmp(name, "gate_tier2")) { c->gate_tier2 = value; return 0; }
+    if (name && !strcmp(name, "r4_full")) { g_asm_r4_full = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "red_groups")) { if (value < 1 || value > kRedGroups) return fail_msg(2, "red_groups outside 1..%d", kRedGroups); c->red_groups = value; return 0; }
     if (name && !strcmp(name, "asm_generic")) {
         c->asm_generic = value;

@@ -41,6 +41,8 @@
 
 namespace bsde {
 
+int g_asm_r4_full = 1;     // option "r4_full": 0 = never take k_assemble_r4's specialised instantiation (A/B measurement)
+
 namespace {
 
 constexpr int kAsmThreads = 128;
@@ -436,6 +438,73 @@ constexpr int kR4WarpDoubles = kR4FmRows * kStride + 32 * kR4SmStride;
 #ifndef BSDE_R4_MIN_BLOCKS
 #define BSDE_R4_MIN_BLOCKS 3
 #endif
+// FULL = the interior launches of a C3..C5 sweep (192 of 196 per sweep at d = 100): fused interface update from a rank-4
+// neighbour, both bonds present with 4 components, N a multiple of 32.  Everything load_raw / fuse_interface decide at run
+// time for the general case (component counts, null bonds, tail masking, clamped sample index: ~150 integer / predicate
+// instructions per 32-sample chunk, ncu source page of round 1) is compiled out; the arithmetic is the same instruction
+// sequence, so the results are bit-identical to the general form.
+template <bool FULL>
+__device__ __forceinline__ void r4_load_raw(const AsmArgs& a, int lane, int64_t chunk, int64_t nchunks, RawSample<4, 4>& r) {
+    if (!FULL) { load_raw<4, 4>(a, lane, chunk, nchunks, r); return; }
+    const int64_t N = a.in.N;
+    if (chunk >= nchunks) chunk = nchunks - 1;            // past the end: a harmless re-read, never staged
+    const int64_t s = chunk * 32 + lane;
+    const double* pl = a.ldL + s;
+    const double* pr = a.ldR + s;
+    r.vm = 1.0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) { r.L[q] = pl[(int64_t)q * N]; r.R[q] = pr[(int64_t)q * N]; }
+    r.xf = a.in.data[(int64_t)a.fj * N + s];
+    r.xb[0] = a.in.data[(int64_t)a.j * N + s];
+    r.y = a.y[s];
+}
+
+template <bool FULL>
+__device__ __forceinline__ void r4_fuse(const AsmArgs& a, const double* __restrict__ core, int64_t s, RawSample<4, 4>& r) {
+    if (!FULL) { if (a.fuse) fuse_interface<4, 4>(a, core, s, r); return; }
+    double phi[4], out[4];
+    monomials_cr<4>(r.xf, phi);
+    const double2* c2 = reinterpret_cast<const double2*>(core);
+    if (a.fuse == 1) {                                   // same operation order as fuse_interface's straight-line form
+#pragma unroll
+        for (int b = 0; b < 4; b++) out[b] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const double t = r.L[q] * phi[m];
+#pragma unroll
+                for (int b = 0; b < 4; b += 2) {
+                    const double2 cv = c2[((q * 4 + m) * 4 + b) >> 1];
+                    out[b] = fma(t, cv.x, out[b]);
+                    out[b + 1] = fma(t, cv.y, out[b + 1]);
+                }
+            }
+#pragma unroll
+        for (int b = 0; b < 4; b++) { r.L[b] = out[b]; a.f_out[(int64_t)b * a.in.N + s] = out[b]; }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                double t = 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; b += 2) {
+                    const double2 cv = c2[((q * 4 + m) * 4 + b) >> 1];
+                    t = fma(cv.x, r.R[b], t);
+                    t = fma(cv.y, r.R[b + 1], t);
+                }
+                acc = fma(phi[m], t, acc);
+            }
+            out[q] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) { r.R[q] = out[q]; a.f_out[(int64_t)q * a.in.N + s] = out[q]; }
+    }
+}
+
+template <bool FULL>
 __global__ void __launch_bounds__(kAsmThreads, BSDE_R4_MIN_BLOCKS)
 k_assemble_r4(AsmArgs a) {
     extern __shared__ double sm[];
@@ -467,15 +536,19 @@ k_assemble_r4(AsmArgs a) {
     const int64_t warps_total = (int64_t)gridDim.x * kAsmWarps;
     RawSample<4, 4> raw;
 #ifndef BSDE_R4_NOPREFETCH
-    load_raw<4, 4>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
+    r4_load_raw<FULL>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
 #endif
     for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
 #ifdef BSDE_R4_NOPREFETCH
-        load_raw<4, 4>(a, lane, chunk, nchunks, raw);      // 4 CTAs per SM: the other warps cover the DRAM latency
+        r4_load_raw<FULL>(a, lane, chunk, nchunks, raw);      // 4 CTAs per SM: the other warps cover the DRAM latency
 #endif
-        if (a.fuse) fuse_interface<4, 4>(a, score, chunk * 32 + lane, raw);
+#ifdef BSDE_R4_EXPERIMENT_PHASE2_ONLY      // measurement only (wrong results): stage the first chunk, then DMMA phases alone
+        if (chunk == (int64_t)blockIdx.x * kAsmWarps + warp)
+#endif
+        {
+        r4_fuse<FULL>(a, score, chunk * 32 + lane, raw);
         {   // ---- phase 1: lane = sample ----
-            const double vm = raw.vm, yv = raw.y * vm;
+            const double vm = FULL ? 1.0 : raw.vm, yv = FULL ? raw.y : raw.y * vm;
             double ll[10], rr[10];
             int idx = 0;
 #pragma unroll
@@ -503,9 +576,10 @@ k_assemble_r4(AsmArgs a) {
             }
             accyy += yv * yv;
         }
-#ifndef BSDE_R4_NOPREFETCH
-        load_raw<4, 4>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
+#if !defined(BSDE_R4_NOPREFETCH) && !defined(BSDE_R4_EXPERIMENT_PHASE2_ONLY)
+        r4_load_raw<FULL>(a, lane, chunk + warps_total, nchunks, raw);      // prefetch the next chunk
 #endif
+        }
         __syncwarp();
         // ---- phase 2: 8 k-steps of 4 samples, 15 DMMA each ----
 #pragma unroll
@@ -709,7 +783,17 @@ constexpr int kRbClassR4 = 100;       // AsmPlan::rb_class of k_assemble_r4
 
 template <int RB, int PB>
 int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* occ) {
-    if (P.rb_class == kRbClassR4) return run_kernel(k_assemble_r4, op, P, a, st, occ);
+    if (P.rb_class == kRbClassR4) {
+        if (op == OP_OCCUPANCY) {          // both instantiations need their shared-memory attribute set
+            const int rc = run_kernel(k_assemble_r4<true>, op, P, a, st, occ);
+            if (rc) return rc;
+            return run_kernel(k_assemble_r4<false>, op, P, a, st, occ);
+        }
+        const bool full = a && a->fuse && a->fr_in == 4 && a->nldL == 4 && a->nldR == 4 && a->ldL && a->ldR && a->in.kind == BASIS_POLY &&
+                          a->in.p == 4 && (a->in.N % 32) == 0 && g_asm_r4_full;
+        if (full) return run_kernel(k_assemble_r4<true>, op, P, a, st, occ);
+        return run_kernel(k_assemble_r4<false>, op, P, a, st, occ);
+    }
     if (P.rb_class >= 0) {
         switch (P.rb_class) {
             case 0: return run_kernel(k_assemble_rb<1, 1, 1, RB, PB>, op, P, a, st, occ);

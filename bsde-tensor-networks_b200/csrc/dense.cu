@@ -1235,6 +1235,15 @@ k_micro_solve(MicroSolveArgs a) {
                 rank = jacobi_eig_lstsq(S, n, S.bvec, xtmp, a.clk ? &s_sweeps : nullptr);
                 if (a.clk && threadIdx.x == 0) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
             } else {
+                // jacobi_lstsq orthogonalises the COLUMNS of the matrix it finds as G[c * n + i]; the expansion wrote A
+                // row-major, which is the same thing only for a symmetric A: transpose a general one first
+                {
+                    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                        const int i = e / n, j = e - i * n;
+                        if (j > i) { const double t = S.G[i * n + j]; S.G[i * n + j] = S.G[j * n + i]; S.G[j * n + i] = t; }
+                    }
+                    __syncthreads();
+                }
                 xtmp = S.red;
                 rank = jacobi_lstsq(S, n, S.bvec, xtmp);
             }

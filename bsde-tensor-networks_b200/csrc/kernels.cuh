@@ -73,6 +73,7 @@ bool asm_fuse_supported(const AsmPlan& plan, const Inputs& in, const FusedInterf
 // Launches the assembly kernel and the partial reduction; `moments` (moment_groups rows of partial_stride doubles, device)
 // receives [M1 (nB,nLL,nRR) | M2 (p,rl,rr) | y.y] as moment_groups partial sums (MicroSolveArgs::moment_rows adds them).
 constexpr int kRedGroups = 6;
+extern int g_asm_r4_full;
 int launch_assembly(const AsmPlan& plan, const Inputs& in, int j, const double* L, const double* R, const double* y,
                     double* partial, double* moments, cudaStream_t st, cudaEvent_t mid = nullptr,
                     const PeerExchange* px = nullptr, const FusedInterface* fi = nullptr, int moment_groups = 1);

@@ -238,3 +238,57 @@ def test_als_errors(backend):
         ALS(phis, np.ones(49), ranks=(1, 2, 2, 1))
     with pytest.raises(BackendError):
         ALS(phis, np.ones(50), ranks=(2, 2, 2, 1))       # boundary rank must be 1
+
+
+def test_specialised_rank4_assembly_is_bit_identical_to_the_general_form(backend):
+    """k_assemble_r4<FULL> (interior launches: rank-4 neighbour, N a multiple of 32; component counts, tail masks and
+    address arithmetic compiled out) must produce the bits of the general instantiation: same cores after the fit."""
+    from bsde_solver._backend import DeviceInputs
+    from bsde_solver._lib import BASIS_POLY
+
+    rng = np.random.RandomState(31)
+    for d, N in ((7, 1 << 15), (12, 96000)):
+        p, ranks = 4, np.array([1] + [4] * (d - 1) + [1], dtype=np.int32)
+        x = rng.randn(N, d) * 0.6
+        y = np.log(0.5 + 0.5 * (x**2).sum(axis=1)) - 0.2 * x[:, 1] * x[:, 2]
+        init = flat([rng.rand(ranks[i], p, ranks[i + 1]) * 2 - 1 for i in range(d)])
+        inp = DeviceInputs(BASIS_POLY, p, backend.to_device(np.ascontiguousarray(x.T)))
+        yd = backend.to_device(y)
+        out = {}
+        try:
+            for full in (1, 0):
+                backend.set_option("r4_full", full)
+                got = init.copy()
+                backend.fit_als(inp, yd, 3, ranks, 0, got)
+                out[full] = got
+        finally:
+            backend.set_option("r4_full", 1)
+        assert np.all(np.isfinite(out[1]))
+        assert np.array_equal(out[0], out[1]), (d, N)
+
+
+def test_moment_reduction_row_groups_agree(backend):
+    """The partial rows of the assembly kernel are summed in 1..6 row groups (k_moment_reduce) that the solve kernel adds
+    while staging; a different grouping is a different (fixed) summation tree: same fit to rounding."""
+    from bsde_solver._backend import DeviceInputs
+    from bsde_solver._lib import BASIS_POLY
+
+    rng = np.random.RandomState(32)
+    d, p, N = 6, 4, 1 << 17
+    ranks = np.array([1] + [4] * (d - 1) + [1], dtype=np.int32)
+    x = rng.randn(N, d) * 0.5
+    y = np.sin(x[:, 0]) + 0.3 * x[:, 1] * x[:, 2] + 0.1 * (x**2).sum(axis=1)
+    init = flat([rng.rand(ranks[i], p, ranks[i + 1]) * 2 - 1 for i in range(d)])
+    inp = DeviceInputs(BASIS_POLY, p, backend.to_device(np.ascontiguousarray(x.T)))
+    yd = backend.to_device(y)
+    fits = {}
+    try:
+        for groups in (1, 3, 6):
+            backend.set_option("red_groups", groups)
+            got = init.copy()
+            backend.fit_als(inp, yd, 3, ranks, 0, got)
+            fits[groups] = backend.tt_eval(inp, ranks, got).cpu().numpy()
+    finally:
+        backend.set_option("red_groups", 3)
+    for groups in (3, 6):
+        assert rel(fits[groups], fits[1]) < 1e-10, groups

@@ -171,6 +171,53 @@ def test_solver_matches_numpy_lstsq(backend):
     assert rel(x, np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-9
 
 
+def test_lstsq_eigen_path_symmetric_and_general_input(backend):
+    """'lstsq' beyond the Cholesky gate: symmetric systems (every micro-step) go through the two-sided Jacobi
+    eigen-decomposition — also indefinite ones, singular values are |lambda| — and non-symmetric input through the
+    one-sided Jacobi SVD.  Graded, numerically rank-deficient Gram matrices of monomial features are the systems that
+    actually reach this path (truncation at eps * n * s_max as numpy.linalg.lstsq, solve.py:11)."""
+    rng = np.random.RandomState(9)
+    # graded Gram matrix with a nearly dependent column: fitted values are what is well defined
+    for n_l, p, n_r in ((4, 4, 4), (2, 3, 2), (3, 3, 3)):
+        N = 4096
+        L = rng.randn(N, n_l) * np.exp(rng.randn(N, 1))
+        R = rng.randn(N, n_r) * np.exp(rng.randn(N, 1))
+        xs = 1.0 + 0.3 * rng.randn(N)
+        V = np.einsum("sa,sm,sb->samb", L, np.stack([xs**k for k in range(p)], axis=1), R).reshape(N, -1)
+        V[:, -1] = V[:, 0] + 1e-9 * V[:, 1]
+        A = V.T @ V
+        A = 0.5 * (A + A.T)
+        b = V.T @ np.log(1.0 + (V[:, :3] ** 2).sum(axis=1))
+        ref, _, rank_ref, _ = np.linalg.lstsq(A, b, rcond=None)
+        x, info = backend.solve(A, b, 0)
+        assert info[1] == 1 and info[3] == rank_ref, (A.shape[0], info.tolist(), rank_ref)
+        assert rel(V @ x, V @ ref) < 1e-9
+        try:                                            # the one-sided SVD on the same system
+            backend.set_option("svd_onesided", 1)
+            x1, info1 = backend.solve(A, b, 0)
+        finally:
+            backend.set_option("svd_onesided", 0)
+        assert info1[3] == rank_ref and rel(V @ x1, V @ ref) < 1e-9
+    # symmetric indefinite, exactly singular (rank n - 3)
+    n = 24
+    Q, _ = np.linalg.qr(rng.randn(n, n))
+    lam = np.concatenate([rng.uniform(0.5, 3.0, n - 3) * rng.choice([-1.0, 1.0], n - 3), np.zeros(3)])
+    A = (Q * lam) @ Q.T
+    A = 0.5 * (A + A.T)
+    b = A @ rng.randn(n)
+    x, info = backend.solve(A, b, 0)
+    assert info[3] == n - 3
+    assert rel(x, np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-10
+    # non-symmetric square system, rank n - 1
+    n = 17
+    M = rng.randn(n, n)
+    M[:, -1] = M[:, 0] - 2.0 * M[:, 3]
+    b = M @ rng.randn(n)
+    x, info = backend.solve(M, b, 0)
+    assert info[3] == n - 1
+    assert rel(x, np.linalg.lstsq(M, b, rcond=None)[0]) < 1e-10
+
+
 def test_solver_rejects_unknown_method(backend):
     from bsde_solver._lib import BackendError
     from bsde_solver.core.optimisation.solve import solver
