@@ -293,12 +293,13 @@ def main():
     asm_flops_per_launch = N * per_sweep_flops / (2 * (D - 1))                 # average over the sweep's launches
     achieved = asm_flops_per_launch / (asm_ms / asm_n * 1e-3) / 1e12
     total_prof = sum(v[0] for v in stats.values())
-    roofline = {"kernel": "k_assemble (normal-equation moments on the FP64 tensor pipe, mma.sync m8n8k4 f64)",
+    roofline = {"kernel": "k_assemble_r4 (normal-equation moments on the FP64 tensor pipe, mma.sync m8n8k4 f64 = DMMA.8x8x4; interface update of the previous micro-step fused in)",
                 "bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
                 "peak_source": "FP64 DMMA peak measured on this pool by bench/micro/fp64_peak.cu (profiles/fp64_peak_r01.txt); MEASURED_PEAKS.json has no FP64 figure",
                 "avg_launch_us": 1e3 * asm_ms / asm_n, "launches_timed": asm_n,
                 "algorithmic_flops_per_launch": asm_flops_per_launch,
+                "algorithmic_bytes_per_launch": N * (88 + 32),
                 "note": "achieved counts the reference algorithm's n(n+1)+2n flops per sample; the kernel executes ~0.36x of them (Kronecker moment factorisation), so frac can exceed 1",
                 "share_of_step": {k: v[0] / total_prof for k, v in stats.items()},
                 "class_us_per_launch": {k: (1e3 * v[0] / v[1] if v[1] else None) for k, v in stats.items()},

@@ -16,7 +16,7 @@ cap() {   # name, kernel regex, launches to skip, launches to take
     ncu -i /tmp/$1.ncu-rep --page source --csv 2>/dev/null | gzip > $out/$1_source.csv.gz
     rm -f /tmp/$1.ncu-rep
 }
-cap asm 'k_assemble_r4' 6 1
+cap asm 'k_assemble_r4' 8 1
 cap solve 'k_micro_solve_fast' 6 1
 cap reduce 'k_moment_reduce' 6 1
 ls -la $out
