@@ -350,9 +350,11 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     BSDE_TRY(get_plan(c, rl, T.p, rr, m.mono, m.in->N, &P));
     BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
     BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride * kRedGroups));
-    // single GPU: the partial rows are summed in kRedGroups groups, added up by the solve kernel; sharded: one group (the
-    // all-reduce, fused or NCCL, works on the complete sums)
-    const int groups = (c->world > 1 || P->grid_x < 8 * kRedGroups) ? 1 : (int)c->red_groups;
+    // the partial rows are summed in `groups` row groups, added up by the solve kernel while staging.  Sharded runs
+    // all-reduce every group row on its own (fused exchange: one flag per (group, block); NCCL: groups * stride doubles),
+    // so the replicas still add identical numbers in identical order.
+    int groups = P->grid_x < 8 * kRedGroups ? 1 : (int)c->red_groups;
+    if (c->world > 1 && c->px_on && (int64_t)groups * ((P->partial_stride + 31) / 32) > kXBlocks) groups = 1;
     if (fi && fi->side && !asm_fuse_supported(*P, *m.in, *fi)) {      // this shape cannot fuse: separate interface kernel
         cudaEvent_t i0 = prof_mark(c);
         if (fi->side == 1) BSDE_TRY(launch_interface_left(*m.in, fi->j, fi->core, fi->r_in, rl, fi->in, fi->out, c->stream));
@@ -370,7 +372,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     prof_span(c, bsde_ctx::P_REDUCE, e1, e2);
     cudaEvent_t e3 = e2;
     if (c->world > 1 && !c->px_on) {          // NCCL path; with the peer exchange the all-reduce is inside the reduce kernel
-        BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), (int)P->partial_stride));
+        BSDE_TRY(allreduce_moments(c, c->moments.as<double>(), (int)P->partial_stride * groups));
         e3 = prof_mark(c);
         prof_span(c, bsde_ctx::P_ALLREDUCE, e2, e3);
     }

@@ -738,16 +738,17 @@ k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, in
         // flag per (source rank, block), wait for the same block of every other rank, add in rank order.  Every rank
         // adds the same numbers in the same order, so all replicas end with bit-identical sums.  Buffers alternate
         // with the parity of the launch count: a rank can only be one exchange ahead of the slowest one.
-        const unsigned long long seq = px.step[blockIdx.x] + 1;
+        const int bid = blockIdx.y * gridDim.x + blockIdx.x;          // (row group, slot block): every group is exchanged on its own
+        const unsigned long long seq = px.step[bid] + 1;
         const size_t par = (size_t)(seq & 1ull) * px.world;
-        const int slot = blockIdx.x * 32 + lane;
+        const int slot = bid * 32 + lane;
         for (int p = 0; p < px.world; p++) px.data[p][(par + px.rank) * kXSlots + slot] = t;
         __threadfence_system();
         __syncwarp();
         if (lane < px.world)
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[lane] + (par + px.rank) * kXBlocks + blockIdx.x), "l"(seq) : "memory");
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[lane] + (par + px.rank) * kXBlocks + bid), "l"(seq) : "memory");
         if (lane < px.world) {
-            const unsigned long long* f = px.flags[px.rank] + (par + lane) * kXBlocks + blockIdx.x;
+            const unsigned long long* f = px.flags[px.rank] + (par + lane) * kXBlocks + bid;
             const long long t0 = clock64();
             unsigned long long v;
             do {
@@ -758,7 +759,7 @@ k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, in
         __syncwarp();
         t = 0.0;
         for (int q = 0; q < px.world; q++) t += __ldcg(px.data[px.rank] + (par + q) * kXSlots + slot);
-        if (lane == 0) px.step[blockIdx.x] = seq;
+        if (lane == 0) px.step[bid] = seq;
     }
     if (e < n_slots) sums[e] = t;
 }
@@ -1060,10 +1061,11 @@ int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, 
     const int red_blocks = (int)((P.partial_stride + 31) / 32);
     PeerExchange ex;
     if (px && px->world > 1) {
-        if (red_blocks > kXBlocks || red_blocks * 32 > kXSlots) return fail_msg(2, "assembly: %d reduce blocks exceed the peer-exchange buffer", red_blocks);
+        if (red_blocks * moment_groups > kXBlocks || red_blocks * moment_groups * 32 > kXSlots)
+            return fail_msg(2, "assembly: %d x %d reduce blocks exceed the peer-exchange buffer", red_blocks, moment_groups);
         ex = *px;
     }
-    if (moment_groups < 1 || (ex.world > 1 && moment_groups != 1)) return fail_msg(2, "assembly: %d moment groups", moment_groups);
+    if (moment_groups < 1 || moment_groups > kRedGroups) return fail_msg(2, "assembly: %d moment groups", moment_groups);
     k_moment_reduce<<<dim3(red_blocks, moment_groups), 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride,
                                                                                (int)P.partial_stride, moments, ex);
     BSDE_CUDA_OK(cudaGetLastError());
