@@ -891,11 +891,11 @@ __device__ __forceinline__ bool fast_pair_step(const FastTile& ft, double (&e)[3
     return false;
 }
 
-// Second-tier acceptance test of k_micro_solve_fast (see the call site): warp 0 estimates sigma_min(A) by two more
+// Second-tier acceptance test of k_micro_solve_fast (see the call site): warp 0 estimates sigma_min(A) by three more
 // inverse iterations with the factor A_s = L~ D L~^T (A_s = S A S, S = diag(sc)) starting from A^-1 e (pv), and
-// sigma_max(A) by five power iterations on A read back from the staged moments.  Lane l carries rows l and l + 32.
+// sigma_max(A) by six power iterations on A read back from the staged moments.  Lane l carries rows l and l + 32.
 // Returns (uniformly) whether sigma_min / sigma_max > kGate2 * eps * n.
-constexpr double kGate2 = 2.0;
+constexpr double kGate2 = 1.25;
 __device__ bool fast_second_tier(const MicroSolveArgs& a, int n, int np, int ld, const double* __restrict__ Lr,
                                  const double* __restrict__ sc, const double* __restrict__ dinv, double* pv,
                                  const double* __restrict__ stage, double* s_red) {
@@ -906,7 +906,7 @@ __device__ bool fast_second_tier(const MicroSolveArgs& a, int n, int np, int ld,
         const bool f0 = lane < np, f1 = lane + 32 < np;
         double w0 = h0 ? pv[lane] : 0.0, w1 = h1 ? pv[lane + 32] : 0.0;
         double grow = 0.0;
-        for (int it = 0; it < 2; it++) {
+        for (int it = 0; it < 3; it++) {
             const double inv = rsqrt(warp_sum(fma(w0, w0, w1 * w1)));
             double z0 = h0 ? w0 * inv * sc[lane] : 0.0, z1 = h1 ? w1 * inv * sc[lane + 32] : 0.0;
 #pragma unroll 4
@@ -938,7 +938,7 @@ __device__ bool fast_second_tier(const MicroSolveArgs& a, int n, int np, int ld,
         if (h1) pv[lane + 32] = 1.0 / sc[lane + 32];
         __syncwarp();
         double rq = 0.0;
-        for (int it = 0; it < 5; it++) {
+        for (int it = 0; it < 6; it++) {
             double u0 = 0.0, u1 = 0.0;
             if (h0) { const uint16_t* m0 = map + lane * n; for (int j = 0; j < n; j++) u0 = fma(stage[m0[j]], pv[j], u0); }
             if (h1) { const uint16_t* m1 = map + (lane + 32) * n; for (int j = 0; j < n; j++) u1 = fma(stage[m1[j]], pv[j], u1); }
@@ -1135,11 +1135,11 @@ k_micro_solve_fast(MicroSolveArgs a) {
             // ---- second tier.  The first test is cheap but loose (trace >= sigma_max by up to n, one probe solve, safety
             // 100): at N >= 2^21 samples a tenth of the C3 micro-steps fail it although lstsq truncates nothing (measured:
             // cond 10^12.4 .. 10^13.6 against the truncation threshold 1/(eps n) = 10^13.85), and each of them costs an
-            // eigen-decomposition.  Here both ends of the spectrum are estimated properly: sigma_max by five power
-            // iterations on A (Rayleigh quotient, a lower bound that is tight for these matrices), sigma_min by two more
+            // eigen-decomposition.  Here both ends of the spectrum are estimated properly: sigma_max by six power
+            // iterations on A (Rayleigh quotient, a lower bound that is tight for these matrices), sigma_min by three more
             // inverse iterations on the factor we already hold.  The exact solve is accepted when the estimated ratio
-            // stays kGate2 = 2 above eps n (LAPACK's own sigma_min carries a relative error of a few percent there:
-            // eps sigma_max against sigma_min ~ eps n sigma_max — closer to the threshold its decision is noise too).
+            // stays kGate2 = 1.25 above eps n (LAPACK's own sigma_min carries an absolute error of a few eps sigma_max, i.e.
+            // a few percent of sigma_min ~ eps n sigma_max: closer to the threshold its decision is noise too).
             ok = fast_second_tier(a, n, np, ld, Lr, sc, dinv, pv, stage, s_red);
         }
 #ifdef BSDE_DEBUG_JACOBI

@@ -62,7 +62,9 @@ BSDE_API int bsde_ctx_sync(bsde_ctx* ctx);
 /* kernels launched by this context so far (bench.py's gpu_launches) */
 BSDE_API int bsde_ctx_launch_count(bsde_ctx* ctx, int64_t* out);
 /* options: "use_graph" (CUDA graph per ALS sweep, default 1); "profile" (1 = time every eager kernel launch with
- * CUDA events by class and disable graphs; setting it resets the counters) */
+ * CUDA events by class and disable graphs; setting it resets the counters); measurement switches with the product path
+ * as default, listed in INTEGRATION.md §4: "fuse_interface", "fast_solve", "gate_tier2", "svd_onesided", "red_groups",
+ * "r4_full", "asm_generic", "solve_stop" */
 BSDE_API int bsde_ctx_set_option(bsde_ctx* ctx, const char* name, int64_t value);
 /* stats: "<class>_ms" / "<class>_n" for class in assembly, reduce, allreduce, solve, interface (device time and
  * launch count accumulated while "profile" is on); "solve_phase0".."solve_phase3" (SM cycles spent by the solve
