@@ -582,7 +582,11 @@ k_assemble_r4(AsmArgs a) {
         }
         __syncwarp();
         // ---- phase 2: 8 k-steps of 4 samples, 15 DMMA each ----
-#pragma unroll
+#ifndef BSDE_R4_UNROLL
+#define BSDE_R4_UNROLL 8
+#endif
+        constexpr int kUnroll = BSDE_R4_UNROLL;
+#pragma unroll kUnroll
         for (int step = 0; step < 8; step++) {
             const double* w = fm + step * 4;
             const double2* sp = smp + step * (4 * kR4SmStride / 2);
