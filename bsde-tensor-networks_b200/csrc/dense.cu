@@ -122,6 +122,8 @@ __device__ void warp_householder_qr_regs(double* M, int m, int k, int ld, double
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool h0 = lane < m, h1 = lane + 32 < m;
+    const bool small = m <= 16;          // lanes 16.. hold zeros: their partial sums are zero and every lane below 16 is
+                                         // complete after the 8, 4, 2, 1 steps (results are only read from lanes < m)
     double x0[KM], x1[KM], tau[KM];
 #pragma unroll
     for (int c = 0; c < KM; c++) {
@@ -133,7 +135,12 @@ __device__ void warp_householder_qr_regs(double* M, int m, int k, int ld, double
     for (int c = 0; c < KM; c++) {
         if (c >= k) break;
         double ss = ((lane > c) ? x0[c] * x0[c] : 0.0) + x1[c] * x1[c];
-        ss = warp_sum(ss);
+        if (small) {                                          // rows live in lanes 0..15 only: four butterfly steps
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(full, ss, o);
+        } else {
+            ss = warp_sum(ss);
+        }
         const double alpha = __shfl_sync(full, x0[c], c);
         double t = 0.0, beta = alpha, scale = 0.0;
         if (ss != 0.0) {
@@ -152,10 +159,12 @@ __device__ void warp_householder_qr_regs(double* M, int m, int k, int ld, double
 #pragma unroll
         for (int cc = 0; cc < KM; cc++) w[cc] = (cc > c && cc < k) ? fma(v0, x0[cc], v1 * x1[cc]) : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+        for (int o = 16; o > 0; o >>= 1) {
+            if (o == 16 && small) continue;
 #pragma unroll
             for (int cc = 0; cc < KM; cc++)
                 if (cc > c) w[cc] += __shfl_xor_sync(full, w[cc], o);
+        }
 #pragma unroll
         for (int cc = 0; cc < KM; cc++)
             if (cc > c && cc < k) {
@@ -180,10 +189,12 @@ __device__ void warp_householder_qr_regs(double* M, int m, int k, int ld, double
 #pragma unroll
         for (int cc = 0; cc < KM; cc++) w[cc] = (cc >= c && cc < k) ? fma(v0, q0[cc], v1 * q1[cc]) : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+        for (int o = 16; o > 0; o >>= 1) {
+            if (o == 16 && small) continue;
 #pragma unroll
             for (int cc = 0; cc < KM; cc++)
                 if (cc >= c) w[cc] += __shfl_xor_sync(full, w[cc], o);
+        }
 #pragma unroll
         for (int cc = 0; cc < KM; cc++)
             if (cc >= c && cc < k) {
@@ -1172,9 +1183,9 @@ k_micro_solve_fast(MicroSolveArgs a) {
     }
     BSDE_PHASE(1);
     if (a.stop_after == 3) return;
-    if (tid == 0) {
+    if (tid == 64) {                          // not warp 0: it runs the QR next and would wait for these round trips
         *a.fast_flag = 0;
-        if (a.info) { a.info[0] += 1; if (n < a.info[3]) a.info[3] = n; }
+        if (a.info) { atomicAdd(a.info, 1); atomicMin(a.info + 3, n); }
     }
     orthogonalise_and_push(a, n, xs, Lr /* the factor is not needed any more */, W, qrR, tau, vbuf, t_phase);
 }
