@@ -116,6 +116,11 @@ struct bsde_ctx {
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
     bool capturing = false;
+    // host-buffer fits (bsde_fit_als_host): the inputs arrive asset by asset on a copy stream, in the order the right
+    // interfaces are built (d-1 .. 1, then asset 0 and y), so that build_right overlaps the tail of the transfer
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> in_ev;      // in_ev[j]: asset j has arrived; in_ev[d]: y has arrived
+    int in_ev_count = 0;                 // > 0: the current fit must wait on them
     // fused NVLink all-reduce (bsde_comm_p2p_*): buffers of this rank and the peers' mappings
     PeerExchange px;
     bool px_on = false;
@@ -266,6 +271,7 @@ int bonds_alloc(bsde_ctx* c, const Train& T, int64_t N, Bonds& B) {
 // R_{j-1} for j = d-1 .. stop  (bond[j] <- core_j applied to bond[j+1])
 int build_right(bsde_ctx* c, const Train& T, const Inputs& in, const Bonds& B, int stop) {
     for (int j = T.d - 1; j >= stop && j >= 1; j--) {
+        if (c->in_ev_count > j) BSDE_CUDA_OK(cudaStreamWaitEvent(c->stream, c->in_ev[j], 0));
         BSDE_TRY(launch_interface_right(in, j, T.core(j), T.ranks[j], T.ranks[j + 1], j == T.d - 1 ? nullptr : B.at(j + 1),
                                         B.at(j), c->stream));
         c->launches++;
@@ -496,6 +502,8 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
         Bonds B;
         BSDE_TRY(bonds_alloc(c, T, N, B));
         BSDE_TRY(build_right(c, T, in, B, 1));
+        for (int j = 0; j < c->in_ev_count; j++) BSDE_CUDA_OK(cudaStreamWaitEvent(c->stream, c->in_ev[j], 0));
+        c->in_ev_count = 0;
         MicroCtx m{&T, &in, &B, y_dev, solver_id, basis_kind == BASIS_POLY ? 1 : 0, info};
         int it = 0;
         const int fused = (c->fuse_interface && basis_kind != BASIS_PHI) ? 1 : 0;
@@ -720,6 +728,8 @@ int bsde_ctx_destroy(bsde_ctx* c) {
     if (c->px_data_local) cudaFree(c->px_data_local);
     if (c->px_flags_local) cudaFree(c->px_flags_local);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->in_ev) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->own);
     delete c;
     return 0;
@@ -925,10 +935,36 @@ int bsde_fit_als_host(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, cons
     const size_t in_bytes = sizeof(double) * (size_t)d * (basis_kind == BSDE_BASIS_PHI ? p : 1) * (size_t)N;
     BSDE_TRY(c->in_copy.ensure(in_bytes));
     BSDE_TRY(c->y_copy.ensure(sizeof(double) * (size_t)N));
-    BSDE_CUDA_OK(cudaMemcpyAsync(c->in_copy.p, inputs_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    BSDE_CUDA_OK(cudaMemcpyAsync(c->y_copy.p, y_host, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
-    return fit_als(c, basis_kind, d, p, N, c->in_copy.as<double>(), coef_host, c->y_copy.as<double>(), n_iter, ranks, solver_id,
-                   cores_host, info_host);
+    if (d >= 2 && c->world == 1) {
+        if (!c->copy_stream) BSDE_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        while ((int)c->in_ev.size() < d + 2) {
+            cudaEvent_t e;
+            BSDE_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->in_ev.push_back(e);
+        }
+        // the copy stream starts after whatever the context's stream still does with the staging buffers
+        BSDE_CUDA_OK(cudaEventRecord(c->in_ev[d + 1], c->stream));
+        BSDE_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->in_ev[d + 1], 0));
+        const size_t chunk = in_bytes / (size_t)d;                       // one asset: N values, or its p basis rows
+        for (int j = d - 1; j >= 0; j--) {
+            BSDE_CUDA_OK(cudaMemcpyAsync((char*)c->in_copy.p + (size_t)j * chunk, (const char*)inputs_host + (size_t)j * chunk, chunk,
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+            BSDE_CUDA_OK(cudaEventRecord(c->in_ev[j], c->copy_stream));
+        }
+        BSDE_CUDA_OK(cudaMemcpyAsync(c->y_copy.p, y_host, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->copy_stream));
+        BSDE_CUDA_OK(cudaEventRecord(c->in_ev[d], c->copy_stream));
+        c->in_ev_count = d + 1;
+    } else {
+        BSDE_CUDA_OK(cudaMemcpyAsync(c->in_copy.p, inputs_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        BSDE_CUDA_OK(cudaMemcpyAsync(c->y_copy.p, y_host, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
+    }
+    const int rc = fit_als(c, basis_kind, d, p, N, c->in_copy.as<double>(), coef_host, c->y_copy.as<double>(), n_iter, ranks, solver_id,
+                           cores_host, info_host);
+    if (c->in_ev_count) {            // the fit returned before consuming the events (error path): do not leave copies in flight
+        cudaStreamSynchronize(c->copy_stream);
+        c->in_ev_count = 0;
+    }
+    return rc;
 }
 
 int bsde_fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
