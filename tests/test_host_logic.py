@@ -127,3 +127,18 @@ def test_hot_path_does_not_touch_tensor_network_contract(monkeypatch):
     for mod in (als, utils, derivative):
         src = inspect.getsource(mod)
         assert ".contract(" not in src, mod.__name__
+
+
+def test_sweep_driver_counts_the_algorithmic_flops_of_the_survey():
+    """bench/sweep.py reports fractions of the FP64 peak with the reference algorithm's flop count; the three
+    configurations tabulated in SURVEY.md §8(d) pin the formula (n(n+1)+2n per micro-step plus the interface update)."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_sweep", os.path.join(root, "bench", "sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.flops_per_sample_sweep(100, 4, 4) == 866208       # C3
+    assert mod.flops_per_sample_sweep(10, 2, 3) == 3396          # C2
+    assert mod.flops_per_sample_sweep(500, 4, 4) == 4399008      # C5, d = 500
