@@ -22,6 +22,8 @@ __global__ void k_chain(double* out, long long* cyc, double a, double b) {
         if (OP == 6) x = rsqrt(x) + y;                        // rsqrt sequence
         if (OP == 7) x = 1.0 / x + y;                         // IEEE division sequence
         if (OP == 8) x = sqrt(x) + y;
+        if (OP == 9) { __syncthreads(); x += y; }               // block barrier (+ one DADD)
+        if (OP == 10) x = (double)rsqrtf((float)x) + y;      // fp32 rsqrt seed with conversions
     }
     const long long t1 = clock64();
     if (threadIdx.x == 0) cyc[0] = t1 - t0;
@@ -42,7 +44,7 @@ void run(const char* name, int threads) {
 int main() {
     for (int th : {32, 256, 1024}) {
         run<0>("DFMA", th); run<1>("DADD", th); run<2>("DMUL", th); run<3>("MUFU.RCP64H", th); run<4>("SHFL 64-bit", th);
-        run<5>("FFMA", th); run<6>("rsqrt(x)+y", th); run<7>("1/x+y (IEEE)", th); run<8>("sqrt(x)+y", th);
+        run<5>("FFMA", th); run<6>("rsqrt(x)+y", th); run<7>("1/x+y (IEEE)", th); run<8>("sqrt(x)+y", th); run<9>("__syncthreads + DADD", th); run<10>("cvt+rsqrtf+cvt+DADD", th);
     }
     return 0;
 }

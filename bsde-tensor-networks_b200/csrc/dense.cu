@@ -12,6 +12,7 @@
 //   * right/left orthonormalisation of a whole train            reference: tensor_train.py:34-87
 #include "common.cuh"
 #include "kernels.cuh"
+#include "vh_lstsq.cuh"
 #include <cfloat>
 
 namespace bsde {
@@ -224,6 +225,44 @@ __device__ __forceinline__ double load_moment(const MicroSolveArgs& a, int e) {
     return acc;
 }
 
+// Diagonal entry `row` of the system matrix from the moment value v: the optional diagonal vector / ridge and SALSA's
+// regulariser, added in the reference's order  A += reg (= eta^2 Gamma-term + eta^2 Theta-term);  A += eta I  (als.py:143-174).
+// Gamma term: index (a, i, k) of (r_l, p, r_r) -> gamma[a]^2.  Theta term: the reference flat-reshapes a (r_r, p, r_l)^2
+// tensor, so the diagonal entry e carries theta[e / (p * r_l)]^2.
+__device__ __forceinline__ double regularised_diagonal(const MicroSolveArgs& a, int row, double v) {
+    if (a.reg_diag) v += a.reg_diag[row];
+    v += a.ridge;
+    if (a.eta_ptr) {
+        const double eta = *a.eta_ptr;
+        if (a.gamma && a.theta) {
+            double reg = 0.0;
+            if (a.reg_left) { const double g = a.gamma[row / (a.p * a.rr)]; reg += eta * eta * g * g; }
+            if (a.reg_right) { const double t = a.theta[row / (a.p * a.rl)]; reg += eta * eta * t * t; }
+            v += reg;
+        }
+        v += eta;
+    }
+    return v;
+}
+__device__ __forceinline__ bool has_diagonal_terms(const MicroSolveArgs& a) {
+    return a.reg_diag != nullptr || a.ridge != 0.0 || a.eta_ptr != nullptr;
+}
+
+// Entry (i, j) of the system matrix as vh_lstsq reads it: an explicit matrix (bsde_solve), or the staged moments through
+// the expansion map with the regularised diagonal held in `diag` (n doubles; null = the plain moments).
+struct SystemMatrix {
+    const double* direct;     // n x n row-major or null
+    const double* stage;
+    const uint16_t* map;
+    const double* diag;
+    int n;
+    __device__ __forceinline__ double operator()(int i, int j) const {
+        if (direct) return direct[(size_t)i * n + j];
+        if (i == j && diag) return diag[i];
+        return stage[map[i * n + j]];
+    }
+};
+
 struct SolveScratch {
     double* A;      // (n+1) x (n+1) augmented, row-major, ld = n+1
     double* G;      // n x n column-major (Jacobi)        — aliases A
@@ -252,20 +291,7 @@ __device__ void expand_normal_equations(const MicroSolveArgs& a, double* A, int 
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
         const int row = e / n, col = e - row * n;
         double v = stage[map[e]];
-        if (row == col) {
-            if (a.reg_diag) v += a.reg_diag[row];
-            v += a.ridge;
-            if (a.eta_ptr) {
-                const double eta = *a.eta_ptr;
-                if (a.gamma && a.theta) {
-                    // Gamma term: index (a, i, k) of (r_l, p, r_r) -> gamma[a]^2.  Theta term: the reference flat-reshapes a
-                    // (r_r, p, r_l)^2 tensor, so the diagonal entry e carries theta[e / (p * r_l)]^2  (als.py:143-166)
-                    if (a.reg_left) { const double g = a.gamma[row / (a.p * a.rr)]; v += eta * eta * g * g; }
-                    if (a.reg_right) { const double t = a.theta[row / (a.p * a.rl)]; v += eta * eta * t * t; }
-                }
-                v += eta;
-            }
-        }
+        if (row == col) v = regularised_diagonal(a, row, v);
         A[row * ld + col] = v;
     }
     for (int row = threadIdx.x; row < n; row += blockDim.x) bvec[row] = stage[map[n * n + row]];
@@ -932,7 +958,7 @@ __device__ __forceinline__ bool fast_pair_step(const FastTile& ft, double (&e)[3
 constexpr double kGate2 = 1.25;
 __device__ bool fast_second_tier(const MicroSolveArgs& a, int n, int np, int ld, const double* __restrict__ Lr,
                                  const double* __restrict__ sc, const double* __restrict__ dinv, double* pv,
-                                 const double* __restrict__ stage, double* s_red) {
+                                 const double* __restrict__ stage, const double* __restrict__ dg, double* s_red) {
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     if (tid < 32) {
@@ -974,8 +1000,9 @@ __device__ bool fast_second_tier(const MicroSolveArgs& a, int n, int np, int ld,
         double rq = 0.0;
         for (int it = 0; it < 6; it++) {
             double u0 = 0.0, u1 = 0.0;
-            if (h0) { const uint16_t* m0 = map + lane * n; for (int j = 0; j < n; j++) u0 = fma(stage[m0[j]], pv[j], u0); }
-            if (h1) { const uint16_t* m1 = map + (lane + 32) * n; for (int j = 0; j < n; j++) u1 = fma(stage[m1[j]], pv[j], u1); }
+            // (dg: the diagonal with SALSA's regulariser; equal to the staged moment for ALS, then the correction is zero)
+            if (h0) { const uint16_t* m0 = map + lane * n; for (int j = 0; j < n; j++) u0 = fma(stage[m0[j]], pv[j], u0); u0 = fma(dg[lane] - stage[m0[lane]], pv[lane], u0); }
+            if (h1) { const uint16_t* m1 = map + (lane + 32) * n; for (int j = 0; j < n; j++) u1 = fma(stage[m1[j]], pv[j], u1); u1 = fma(dg[lane + 32] - stage[m1[lane + 32]], pv[lane + 32], u1); }
             const double v0 = h0 ? pv[lane] : 0.0, v1 = h1 ? pv[lane + 32] : 0.0;
             const double vv = warp_sum(fma(v0, v0, v1 * v1)), vu = warp_sum(fma(v0, u0, v1 * u1));
             const double uu = warp_sum(fma(u0, u0, u1 * u1));
@@ -998,6 +1025,15 @@ __device__ bool fast_second_tier(const MicroSolveArgs& a, int n, int np, int ld,
     return s_red[5] != 0.0;
 }
 
+// doubles at the front of k_micro_solve_fast's shared memory: the factorisation's buffers or, once it has been rejected,
+// vh_lstsq's scratch (whichever is larger; even, so that what follows stays 16-byte aligned)
+__host__ __device__ inline size_t fast_front_doubles(int n) {
+    const size_t np = (size_t)((n + 1) & ~1);
+    const size_t fact = 4 * kFastColPitch + 8 + (np + 3) * (np + 4) + 3 * np;
+    const size_t vh = vh_scratch_doubles(n);
+    return ((fact > vh ? fact : vh) + 1) & ~(size_t)1;
+}
+
 __global__ void __launch_bounds__(kFastThreads, 1)
 k_micro_solve_fast(MicroSolveArgs a) {
     extern __shared__ double sm[];
@@ -1010,10 +1046,13 @@ k_micro_solve_fast(MicroSolveArgs a) {
     double* pivbuf = colbuf + 4 * kFastColPitch;   // [2 parities][4]
     double* Lr = pivbuf + 8;                    // (np + 3) x ld: factor rows, two right-hand-side rows, one dummy row
     double* sc = Lr + (size_t)(np + 3) * ld;    // np
-    double* xs = sc + np;                       // np
-    double* dinv = xs + np;                     // np: 1 / D_k
+    double* dinv = sc + np;                     // np: 1 / D_k
     double* pv = dinv + np;                     // np: power-iteration vector (second-tier test)
-    double* W = pv + np;                        // kMaxR*kMaxP*kMaxR
+    // (everything above is dead when the factorisation is rejected: vh_lstsq's scratch overlays it from sm on)
+    double* xs = sm + fast_front_doubles(n);    // np: the solution
+    double* dg = xs + np;                       // np: diagonal of the system (moments + regulariser)
+    double* bv = dg + np;                       // np: right-hand side (truncated path)
+    double* W = bv + np;                        // kMaxR*kMaxP*kMaxR
     double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
     double* tau = qrR + kMaxR * kMaxR;          // kMaxR
     double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
@@ -1057,16 +1096,17 @@ k_micro_solve_fast(MicroSolveArgs a) {
     __syncthreads();
     // ---- equilibration, trace, positivity of the diagonal ----
     if (tid < np) {
-        const double d = tid < n ? stage[dmap] : 1.0;
+        const double d = tid < n ? regularised_diagonal(a, tid, stage[dmap]) : 1.0;
         sc[tid] = rsqrt(d);
-        xs[tid] = d;
+        dg[tid] = d;
+        if (tid < n) bv[tid] = stage[map[n * n + tid]];
     }
     __syncthreads();
     if (tid < 32) {
         double tr = 0.0;
         int bad = 0;
         for (int i = tid; i < n; i += 32) {
-            const double d = xs[i];
+            const double d = dg[i];
             if (!(d > 0.0) || !isfinite(d)) bad = 1;
             tr += d;
         }
@@ -1086,7 +1126,7 @@ k_micro_solve_fast(MicroSolveArgs a) {
                     const int m = midx[ai][bi][r][c];
                     const int j = min(2 * Cw[bi] + c, np - 1);
                     double v = 0.0;
-                    if (m >= 0) v = stage[m];
+                    if (m >= 0) v = (Rw[ai] < NP && 2 * Rw[ai] + r == 2 * Cw[bi] + c) ? dg[j] : stage[m];
                     else if (m == -2) v = 1.0;
                     else if (m == -3) v = (((unsigned)j * 2654435761u) >> 7) & 1u ? 1.0 : -1.0;
                     v *= sc[j];
@@ -1094,10 +1134,15 @@ k_micro_solve_fast(MicroSolveArgs a) {
                     e[ai][bi][r][c] = v;
                 }
     __syncthreads();
-    if (s_red[1] != 0.0) { if (tid == 0) *a.fast_flag = 1; return; }
+    // accepted = the exact LDL^T solve is numpy.linalg.lstsq's answer.  It stops being true on a non-positive diagonal
+    // entry or pivot and when the acceptance tests say that lstsq would truncate; the micro-step is then redone by
+    // vh_lstsq below, in this kernel (round 1 launched k_micro_solve behind every fast kernel for that: a 3 us no-op
+    // launch per micro-step, and a 1.3 ms two-sided Jacobi when it was needed).
+    bool accepted = s_red[1] == 0.0;
     BSDE_PHASE(0);
     long long t_sub = t_phase;
     if (a.stop_after == 1) return;
+    if (accepted) {
 
     // ---- factorisation: column pairs 0..15 (column block 0), then 16.. (column block 1: row block 0 and column
     // block 0 are finished by then, so that half touches a third of the registers) ----
@@ -1122,10 +1167,12 @@ k_micro_solve_fast(MicroSolveArgs a) {
 #ifdef BSDE_DEBUG_JACOBI
     if (failed && tid == 0) printf("fast cholesky pivot failed n=%d\n", n);
 #endif
-    if (failed) { if (tid == 0) *a.fast_flag = 1; return; }      // uniform
+    if (failed) accepted = false;                                // uniform
+    }
     if (a.stop_after == 2) return;
     __syncthreads();
     if (a.clk && tid == 0) { const long long now = clock64(); atomicAdd((unsigned long long*)(a.clk + 5), (unsigned long long)(now - t_sub)); t_sub = now; }
+    if (accepted) {
 
     // ---- back substitution L~^T x = D^-1 L~^-1 rhs: warp 0 -> b, warp 1 -> probe; lane l carries rows l and l + 32 ----
     if (tid < 64) {
@@ -1174,20 +1221,46 @@ k_micro_solve_fast(MicroSolveArgs a) {
             // inverse iterations on the factor we already hold.  The exact solve is accepted when the estimated ratio
             // stays kGate2 = 1.25 above eps n (LAPACK's own sigma_min carries an absolute error of a few eps sigma_max, i.e.
             // a few percent of sigma_min ~ eps n sigma_max: closer to the threshold its decision is noise too).
-            ok = fast_second_tier(a, n, np, ld, Lr, sc, dinv, pv, stage, s_red);
+            ok = fast_second_tier(a, n, np, ld, Lr, sc, dinv, pv, stage, dg, s_red);
         }
 #ifdef BSDE_DEBUG_JACOBI
         if (!ok && tid == 0) printf("fast gate failed n=%d log10(trace/sigma_min_bound)=%.1f tier2 log10(cond)=%.1f\n", n, log10(s_red[0] / sqrt((double)n / zz)), log10(s_red[6] / s_red[7]));
 #endif
-        if (!ok) { if (tid == 0) *a.fast_flag = 1; return; }
+        if (!ok) accepted = false;
+    }
+    }
+    if (a.stop_after == 3) return;
+    if (accepted) {
+        if (tid == 64 && a.info) { atomicAdd(a.info, 1); atomicMin(a.info + 3, n); }   // not warp 0: it runs the QR next
+    } else {
+        // ---- truncated minimum-norm solve (vh_lstsq.cuh); its scratch overlays the factorisation's buffers ----
+        __syncthreads();
+        __shared__ int s_sweeps;
+        const SystemMatrix Amat{nullptr, stage, map, has_diagonal_terms(a) ? dg : nullptr, n};
+        int rank = vh_lstsq<kFastThreads, 8, 4>(Amat, n, bv, xs, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
+        if (rank < 0) {                       // moments that are not a Gram matrix (overflow, NaN): no answer
+            for (int i = tid; i < n; i += kFastThreads) xs[i] = nan("");
+            rank = 0;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            if (a.info) { atomicAdd(a.info + 1, 1); atomicMin(a.info + 3, rank); }
+            if (a.clk) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
+        }
     }
     BSDE_PHASE(1);
-    if (a.stop_after == 3) return;
-    if (tid == 64) {                          // not warp 0: it runs the QR next and would wait for these round trips
-        *a.fast_flag = 0;
-        if (a.info) { atomicAdd(a.info, 1); atomicMin(a.info + 3, n); }
-    }
-    orthogonalise_and_push(a, n, xs, Lr /* the factor is not needed any more */, W, qrR, tau, vbuf, t_phase);
+    orthogonalise_and_push(a, n, xs, sm /* the factorisation's storage is free now */, W, qrR, tau, vbuf, t_phase);
+}
+
+// The eigen-decomposition / SVD fallbacks below keep a second n x n matrix (the vectors) in shared memory: up to this n
+constexpr int kJacobiMaxN = 100;
+
+// doubles of the first shared-memory region of k_micro_solve: the augmented system (+ the Jacobi vectors for small n),
+// overlaid by vh_lstsq's scratch once the Cholesky path has been rejected
+__host__ __device__ inline size_t dense_front_doubles(int n) {
+    const size_t chol = (size_t)(n + 2) * (n + 3) + (n <= kJacobiMaxN ? (size_t)n * n : 0);
+    const size_t vh = vh_scratch_doubles(n);
+    return ((chol > vh ? chol : vh) + 1) & ~(size_t)1;
 }
 
 __global__ void __launch_bounds__(kDenseThreads)
@@ -1199,8 +1272,8 @@ k_micro_solve(MicroSolveArgs a) {
     SolveScratch S;
     S.A = sm;                                   // (n+2) x (n+3): augmented normal equations / Jacobi G / QR work matrix
     S.G = sm;
-    S.V = sm + (size_t)(n + 2) * (n + 3);       // n^2     : Jacobi right vectors
-    S.x = S.V + (size_t)n * n;                  // n
+    S.V = sm + (size_t)(n + 2) * (n + 3);       // n^2     : Jacobi vectors (n <= kJacobiMaxN only)
+    S.x = sm + dense_front_doubles(n);          // n
     S.sc = S.x + n;                             // n
     S.bvec = S.sc + n;                          // n
     S.red = S.bvec + n;                         // n       : Jacobi solution scratch
@@ -1212,10 +1285,6 @@ k_micro_solve(MicroSolveArgs a) {
     __shared__ int s_path, s_rank, s_ok, s_sym, s_sweeps;
     __shared__ double s_red[4], s_wmax[32], s_wdif[32];
 
-    // behind k_micro_solve_fast: nothing to do unless the fast path gave up (then straight to the SVD path)
-    const bool after_fast = a.fast_flag != nullptr;
-    if (after_fast && *a.fast_flag == 0) return;
-
     expand_normal_equations(a, S.A, ld, S.bvec, stage_buf);
     __syncthreads();
     BSDE_PHASE(0);
@@ -1226,24 +1295,19 @@ k_micro_solve(MicroSolveArgs a) {
     __syncthreads();
     if (a.solver == SOLVER_LSTSQ) {
         {
-            const bool ok = after_fast ? false : cholesky_solve(S, n, S.x, s_red);
-            if (threadIdx.x == 0) { s_ok = ok ? 1 : 0; s_path = ok ? 0 : 1; s_rank = n; }
+            const bool ok = cholesky_solve(S, n, S.x, s_red);
+            if (threadIdx.x == 0) { s_ok = ok ? 1 : 0; s_path = ok ? 0 : 1; s_rank = n; s_sym = 1; }
         }
         __syncthreads();
         if (!s_ok) {
-            // rebuild A (column-major == row-major, A is symmetric) with ld = n for the Jacobi path
-            expand_normal_equations(a, S.G, n, S.bvec, stage_buf);
-            __syncthreads();
-            // symmetric (every micro-step; bsde_solve callers normally too): two-sided Jacobi on A.  Anything else: the
-            // general one-sided SVD.  The test is exact for the moment expansion and tolerant of a rounded host matrix.
-            if (threadIdx.x == 0) s_sym = 1;
-            __syncthreads();
-            {
+            // Moment matrices are symmetric by construction.  An explicit system (bsde_solve) is tested: symmetric ones
+            // take the same path, anything else the general one-sided SVD.  Tolerant of a rounded host matrix.
+            if (a.A_direct) {
                 double amax = 0.0, dmax = 0.0;
                 for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
                     const int i = e / n, j = e - i * n;
                     if (j > i) continue;
-                    const double u = S.G[i * n + j], v = S.G[j * n + i];
+                    const double u = a.A_direct[i * n + j], v = a.A_direct[j * n + i];
                     amax = fmax(amax, fmax(fabs(u), fabs(v)));
                     dmax = fmax(dmax, fabs(u - v));
                 }
@@ -1253,33 +1317,54 @@ k_micro_solve(MicroSolveArgs a) {
                 if (threadIdx.x == 0) {
                     double a2 = 0.0, d2 = 0.0;
                     for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a2 = fmax(a2, s_wmax[w]); d2 = fmax(d2, s_wdif[w]); }
-                    s_sym = (a.force_onesided == 0 && d2 <= 8.0 * DBL_EPSILON * a2) ? 1 : 0;
+                    s_sym = (d2 <= 8.0 * DBL_EPSILON * a2) ? 1 : 0;
                 }
                 __syncthreads();
             }
-            int rank;
-            double* xtmp;
-            if (s_sym) {
-                for (int e = threadIdx.x; e < n * n; e += blockDim.x) {          // exact symmetry: mirror the lower triangle
-                    const int i = e / n, j = e - i * n;
-                    if (j > i) S.G[i * n + j] = S.G[j * n + i];
-                }
+            int rank = -1;
+            double* xtmp = S.red;
+            if (s_sym && !a.force_onesided) {
+                // positive semi-definite systems (every normal-equation matrix): pivoted Cholesky + one-sided Jacobi on the
+                // factor (vh_lstsq.cuh).  Its scratch overlays S.A, so the entries are read through the expansion again;
+                // the regularised diagonal is parked in S.sc.
+                const bool diag = !a.A_direct && has_diagonal_terms(a);
+                if (diag)      // (S.A was scaled and factorised in place by the rejected Cholesky attempt)
+                    for (int i = threadIdx.x; i < n; i += blockDim.x) S.sc[i] = regularised_diagonal(a, i, stage_buf[a.expand_map[i * n + i]]);
                 __syncthreads();
-                xtmp = S.A + (size_t)n * n;          // S.sc / S.red hold the rotations; G uses n*n of the (n+2) x (n+3) storage
-                rank = jacobi_eig_lstsq(S, n, S.bvec, xtmp, a.clk ? &s_sweeps : nullptr);
-                if (a.clk && threadIdx.x == 0) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
-            } else {
-                // jacobi_lstsq orthogonalises the COLUMNS of the matrix it finds as G[c * n + i]; the expansion wrote A
-                // row-major, which is the same thing only for a symmetric A: transpose a general one first
-                {
-                    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-                        const int i = e / n, j = e - i * n;
-                        if (j > i) { const double t = S.G[i * n + j]; S.G[i * n + j] = S.G[j * n + i]; S.G[j * n + i] = t; }
-                    }
+                const SystemMatrix Amat{a.A_direct, stage_buf, a.expand_map, diag ? S.sc : nullptr, n};
+                rank = vh_lstsq<kDenseThreads, 32, 3>(Amat, n, S.bvec, xtmp, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
+                if (rank >= 0 && a.clk && threadIdx.x == 0) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
+            }
+            if (rank < 0) {
+                // symmetric but indefinite (or A/B option svd_onesided), or not symmetric at all: the round-1 paths, for
+                // the sizes whose vectors fit beside the matrix
+                if (n > kJacobiMaxN) {
+                    for (int i = threadIdx.x; i < n; i += blockDim.x) xtmp[i] = nan("");
+                    rank = 0;
                     __syncthreads();
+                } else {
+                    expand_normal_equations(a, S.G, n, S.bvec, stage_buf);      // ld = n for the Jacobi kernels
+                    __syncthreads();
+                    if (s_sym && !a.force_onesided) {
+                        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {      // exact symmetry: mirror the lower triangle
+                            const int i = e / n, j = e - i * n;
+                            if (j > i) S.G[i * n + j] = S.G[j * n + i];
+                        }
+                        __syncthreads();
+                        xtmp = S.A + (size_t)n * n;      // S.sc / S.red hold the rotations; G uses n*n of the (n+2) x (n+3) storage
+                        rank = jacobi_eig_lstsq(S, n, S.bvec, xtmp, a.clk ? &s_sweeps : nullptr);
+                    } else {
+                        // jacobi_lstsq orthogonalises the COLUMNS of the matrix it finds as G[c * n + i]; the expansion
+                        // wrote A row-major, which is the same thing only for a symmetric A: transpose a general one first
+                        for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+                            const int i = e / n, j = e - i * n;
+                            if (j > i) { const double t = S.G[i * n + j]; S.G[i * n + j] = S.G[j * n + i]; S.G[j * n + i] = t; }
+                        }
+                        __syncthreads();
+                        xtmp = S.red;
+                        rank = jacobi_lstsq(S, n, S.bvec, xtmp);
+                    }
                 }
-                xtmp = S.red;
-                rank = jacobi_lstsq(S, n, S.bvec, xtmp);
             }
             for (int i = threadIdx.x; i < n; i += blockDim.x) S.x[i] = xtmp[i];
             if (threadIdx.x == 0) s_rank = rank;
@@ -1291,9 +1376,9 @@ k_micro_solve(MicroSolveArgs a) {
     }
     __syncthreads();
     BSDE_PHASE(1);
-    if (threadIdx.x == 0 && a.info) {          // counters: [0] cholesky, [1] jacobi, [2] lu, [3] min numerical rank
-        a.info[s_path] += 1;
-        if (s_rank < a.info[3]) a.info[3] = s_rank;
+    if (threadIdx.x == 0 && a.info) {          // counters: [0] cholesky, [1] truncated (eigen / SVD), [2] lu, [3] min numerical rank
+        atomicAdd(a.info + s_path, 1);
+        atomicMin(a.info + 3, s_rank);
     }
 
     orthogonalise_and_push(a, n, S.x, S.A /* the factorisation storage is free now */, W, qrR, tau, vbuf, t_phase);
@@ -1365,39 +1450,47 @@ k_orthonormalize(OrthoArgs a) {
 
 }  // namespace
 
+// The opt-in shared-memory limit is a per-device attribute of a kernel: set it once for every device a context launches on
+// (the C ABI allows one context per GPU in one process).
+static int set_smem_attributes() {
+    static bool done[64] = {};
+    int dev = 0;
+    BSDE_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done[dev]) return 0;
+    BSDE_CUDA_OK(cudaFuncSetAttribute(k_micro_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    BSDE_CUDA_OK(cudaFuncSetAttribute(k_micro_solve_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return 0;
+}
+
+#define BSDE_TRY_RC(expr) do { const int _rc = (expr); if (_rc) return _rc; } while (0)
+
 int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_launches) {
     const int n = a.rl * a.p * a.rr;
     if (n > kMaxN) return fail_msg(2, "micro_solve: n = %d unknowns exceeds the in-CTA solver limit %d", n, kMaxN);
     if (a.direction > 0 && a.rl * a.p < a.rr) return fail_msg(2, "micro_solve: left QR needs r_j*p >= r_{j+1} (%d*%d < %d)", a.rl, a.p, a.rr);
     if (a.direction < 0 && a.p * a.rr < a.rl) return fail_msg(2, "micro_solve: right QR needs p*r_{j+1} >= r_j (%d*%d < %d)", a.p, a.rr, a.rl);
     // keep in sync with the layout at the top of k_micro_solve
-    const size_t doubles = (size_t)(n + 2) * (n + 3) + (size_t)n * n + 4 * (size_t)n + kMaxR * kMaxP * kMaxR +
-                           kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16 + (size_t)(a.n_slots > 0 ? a.n_slots : 0) + 16;
+    const size_t doubles = dense_front_doubles(n) + 4 * (size_t)n + kMaxR * kMaxP * kMaxR + kMaxR * kMaxR + kMaxR +
+                           kMaxR * kMaxP + 16 + (size_t)(a.n_slots > 0 ? a.n_slots : 0) + 16;
     const size_t bytes = doubles * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        BSDE_CUDA_OK(cudaFuncSetAttribute(k_micro_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        BSDE_CUDA_OK(cudaFuncSetAttribute(k_micro_solve_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
-    if (bytes > 220 * 1024) return fail_msg(2, "micro_solve: n = %d needs %zu B of shared memory", n, bytes);
-    MicroSolveArgs b = a;
-    // plain ALS micro-step of at most 64 unknowns: the register-resident kernel first, k_micro_solve behind it as the
-    // fallback that returns at once unless the fast path gave up
-    const bool fast = a.fast_flag && a.solver == SOLVER_LSTSQ && n <= 64 && !a.reg_diag && !a.eta_ptr && a.ridge == 0.0 &&
-                      !a.A_direct && !a.dbg_A && a.n_slots > 0;
+    BSDE_TRY_RC(set_smem_attributes());
+    // plain micro-step of at most 64 unknowns (ALS and SALSA): the register-resident kernel, which also holds the
+    // truncated path; everything else (larger cores, LU, explicit systems, the parity dump) goes to k_micro_solve
+    const bool fast = a.fast_flag && a.solver == SOLVER_LSTSQ && n <= 64 && !a.A_direct && !a.dbg_A && a.n_slots > 0 && !a.force_onesided;
     if (fast) {
         const int np = (n + 1) & ~1;
-        const size_t fd = (size_t)(np + 3) * (np + 4) + 4 * (size_t)np + 4 * kFastColPitch + 8 + kMaxR * kMaxP * kMaxR +
-                          kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16 + (size_t)a.n_slots + 16;
+        const size_t fd = fast_front_doubles(n) + 3 * (size_t)np + kMaxR * kMaxP * kMaxR + kMaxR * kMaxR + kMaxR +
+                          kMaxR * kMaxP + 16 + (size_t)a.n_slots + 16;
+        if (fd * sizeof(double) > 100 * 1024) return fail_msg(2, "micro_solve: %zu B of shared memory for the fast kernel", fd * sizeof(double));
         k_micro_solve_fast<<<1, kFastThreads, fd * sizeof(double), st>>>(a);
         BSDE_CUDA_OK(cudaGetLastError());
     } else {
-        b.fast_flag = nullptr;
+        if (bytes > 220 * 1024) return fail_msg(2, "micro_solve: n = %d needs %zu B of shared memory", n, bytes);
+        k_micro_solve<<<1, kDenseThreads, bytes, st>>>(a);
+        BSDE_CUDA_OK(cudaGetLastError());
     }
-    k_micro_solve<<<1, kDenseThreads, bytes, st>>>(b);
-    BSDE_CUDA_OK(cudaGetLastError());
-    if (extra_launches) *extra_launches = fast ? 1 : 0;
+    if (extra_launches) *extra_launches = 0;
     return 0;
 }
 

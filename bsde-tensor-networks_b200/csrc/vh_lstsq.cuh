@@ -1,0 +1,341 @@
+// Truncated minimum-norm solve of a symmetric positive semi-definite system inside one CTA — the part of
+// solver(A, b, 'lstsq') (reference: core/optimisation/solve.py:11, numpy.linalg.lstsq(rcond=None)) that the Cholesky fast
+// path cannot serve: normal equations whose spectrum reaches the truncation threshold eps * n * lambda_max.
+//
+//   x = sum_{lambda_i > eps n lambda_max}  v_i (v_i . b) / lambda_i          (A = V diag(lambda) V^T)
+//
+// Method (Veselic-Hari): diagonally pivoted Cholesky A ~ L L^T (L: n x r, stopped when the largest remaining pivot is
+// rounding noise), then ONE-sided Jacobi on the columns of L:  L W = G with orthogonal columns g_i, so that
+// lambda_i = |g_i|^2, v_i = g_i / |g_i| and
+//
+//   x = sum_i g_i (g_i . b) / lambda_i^2 .
+//
+// Why this and not a two-sided Jacobi on A (round 1, ~1.3 ms at n = 64): L^T L is one LR step closer to diagonal than
+// L L^T, the sweep count drops from 13-17 to 5-7; a round needs ONE block barrier (column pairs are disjoint) instead of
+// two; the rotations come from three dot products that every lane of the pair's lane group forms itself, so there is no
+// single-warp rotation phase between barriers; the right singular vectors W are never needed.  Backward error of the
+// factorisation is O(eps |A|), the same class as LAPACK's own singular values (measured on ALS systems: the difference
+// to numpy.linalg.lstsq is the difference between numpy.linalg.lstsq and numpy.linalg.eigh).
+//
+// Rows are never swapped: pivot row j_k is only marked, the k-th column of L lives on the rows not yet selected; the
+// Jacobi phase does not care about the order of the rows, and x comes out in the original order.
+#pragma once
+#include <cfloat>
+#include <climits>
+#include <cuda_runtime.h>
+
+namespace bsde {
+
+#ifdef VH_PROFILE
+#define VH_T(idx) do { if (threadIdx.x == 0) { const long long _n = clock64(); S.clk[idx] += _n - vh_t; vh_t = _n; } } while (0)
+#else
+#define VH_T(idx) do { } while (0)
+#endif
+
+struct VhScratch {
+    long long* clk;  // VH_PROFILE only: phase cycle counters of thread 0
+    double* G;       // r columns of pitch ldg (column-major), ldg even
+    int ldg;
+    double* d;       // n   remaining diagonal of the Schur complement
+    double* lam;     // n   squared column norms
+    double* coef;    // n
+    double* red;     // 8
+    int* flags;      // 8
+    unsigned short* tab;   // (m - 1) * m / 2 round-robin pairs, m = n rounded up to even
+};
+
+__host__ __device__ inline int vh_ldg(int n) { return ((n + 1) & ~1) + 8; }
+__host__ __device__ inline size_t vh_scratch_doubles(int n) {
+    const size_t m = (size_t)((n + 1) & ~1);
+    return (size_t)n * vh_ldg(n) + 3 * (size_t)n + 8 + 8 + ((m - 1) * (m / 2) + 3) / 4 + 1;
+}
+
+__device__ __forceinline__ VhScratch vh_carve(double* base, int n) {
+    VhScratch S;
+    S.clk = nullptr;
+    S.ldg = vh_ldg(n);
+    S.G = base;
+    S.d = base + (size_t)n * S.ldg;
+    S.lam = S.d + n;
+    S.coef = S.lam + n;
+    S.red = S.coef + n;
+    S.flags = reinterpret_cast<int*>(S.red + 8);
+    S.tab = reinterpret_cast<unsigned short*>(S.red + 16);
+    return S;
+}
+
+// 1 / sqrt(x) for normal positive x: hardware seed (MUFU.RSQ64H, ~2^-22) and one third-order step
+// y (1 + e/2 + 3 e^2/8), e = 1 - x y^2: relative error ~e^3, i.e. correctly rounded up to the final rounding.
+// 50 cycles of dependent latency instead of the 75 of the library routine (no special-case branches).
+__device__ __forceinline__ double vh_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+__device__ __forceinline__ void vh_rr_pair(int k, int step, int m, int& p, int& q) {   // round-robin tournament
+    if (k == 0) { p = m - 1; q = step; }
+    else { p = (step + k) % (m - 1); q = (step - k + m - 1) % (m - 1); }
+    if (p > q) { const int t = p; p = q; q = t; }
+}
+
+// T    : threads of the CTA (blockDim.x), a multiple of 64
+// LP   : lanes per column pair in the Jacobi phase (power of two, <= 32); blockDim.x / LP pairs are rotated concurrently
+// UMAX : 16-byte row chunks per lane and column, >= ceil(ceil(n / 2) / LP)
+// AFn  : double operator()(int i, int j) — entry of the symmetric matrix
+// Returns the numerical rank (>= 0), or -1 when A is not positive semi-definite to working accuracy (nothing written).
+// All threads of the CTA must call; uses __syncthreads().
+template <int T, int LP, int UMAX, class AFn>
+__device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double* __restrict__ xout, VhScratch S, int* sweeps_out) {
+    static_assert(T % 64 == 0 && T <= 1024 && (LP & (LP - 1)) == 0 && LP <= 32, "thread layout");
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = T >> 5;
+    const int ldg = S.ldg;
+    double* G = S.G;
+    double* d = S.d;
+
+#ifdef VH_PROFILE
+    long long vh_t = clock64();
+#endif
+    // ---------------- diagonally pivoted Cholesky (left-looking, rows unpermuted) ----------------
+    for (int i = tid; i < n; i += T) d[i] = Aat(i, i);
+    for (int e = tid; e < n * ldg; e += T) G[e] = 0.0;
+    __syncthreads();
+    double dmax0 = 0.0;
+    {
+        bool bad = false;
+        for (int i = lane; i < n; i += 32) { const double v = d[i]; dmax0 = fmax(dmax0, v); bad = bad || !isfinite(v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax0 = fmax(dmax0, __shfl_xor_sync(full, dmax0, o));
+        if (__any_sync(full, bad)) {          // non-finite input: the answer is not a number (numpy raises LinAlgError)
+            for (int i = tid; i < n; i += T) xout[i] = nan("");
+            __syncthreads();
+            return 0;
+        }
+    }
+    // pivots at the level of the rounding noise of the Schur complement are not columns of A any more
+    const double tolpiv = (DBL_EPSILON / 16.0) * dmax0;
+    // threads per row in the column update: TPR lanes (stride RPW inside the warp) share one row
+    constexpr int TPR = T / 64 > 32 ? 32 : T / 64;
+    constexpr int RPW = 32 / TPR;
+    const int rowlocal = lane % RPW, sub = lane / RPW;
+    int r = 0;
+    for (int k = 0; k < n; k++) {
+        // every warp finds the pivot itself (no barrier between the search and the update).  One 64-bit key per row:
+        // the diagonal entry with the row index in its 8 lowest mantissa bits (pivot ties within 2^-44 go to the key
+        // order; the pivot VALUE is read back exactly) — one shuffle and one compare per butterfly stage.
+        long long key = LLONG_MIN;
+        for (int i = lane; i < n; i += 32) {
+            const double v = d[i];
+            if (v > 0.0) { const long long kv = (__double_as_longlong(v) & ~0xffll) | (long long)(255 - i); key = kv > key ? kv : key; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(full, key, o); key = ok > key ? ok : key; }
+        if (key == LLONG_MIN) break;                   // nothing positive left (uniform over the CTA)
+        const int jk = 255 - (int)(key & 0xff);
+        const double bv = d[jk];
+        if (!(bv > tolpiv)) break;
+        const double inv = vh_rsqrt(bv), lkk = bv * inv;
+        double* colk = G + (size_t)k * ldg;
+        for (int i0 = warp * RPW; i0 < n; i0 += nwarps * RPW) {
+            const int i = i0 + rowlocal;
+            const bool live = i < n && i != jk && d[i] > -DBL_MAX;          // not selected yet
+            double part = 0.0, part1 = 0.0;
+            if (live) {
+                int t = sub;
+                for (; t + TPR < k; t += 2 * TPR) {
+                    part = fma(G[(size_t)t * ldg + i], G[(size_t)t * ldg + jk], part);
+                    part1 = fma(G[(size_t)(t + TPR) * ldg + i], G[(size_t)(t + TPR) * ldg + jk], part1);
+                }
+                if (t < k) part = fma(G[(size_t)t * ldg + i], G[(size_t)t * ldg + jk], part);
+                part += part1;
+            }
+#pragma unroll
+            for (int o = RPW; o < 32; o <<= 1) part += __shfl_xor_sync(full, part, o);
+            if (sub == 0 && i < n) {
+                if (live) {
+                    const double v = (Aat(i, jk) - part) * inv;
+                    colk[i] = v;
+                    d[i] = fma(-v, v, d[i]);
+                } else if (i == jk) {
+                    colk[i] = lkk;
+                    d[i] = -DBL_MAX;                   // selected: never a pivot again, no entries in later columns
+                }
+            }
+        }
+        __syncthreads();
+        r = k + 1;
+    }
+    // positive semi-definite to working accuracy?  (Gram matrices always are; an explicit system may not be)
+    if (r < n) {
+        if (tid == 0) S.flags[2] = 0;
+        __syncthreads();
+        const int rest = n * n;
+        bool bad = false;
+        for (int e = tid; e < rest; e += T) {
+            const int i = e / n, j = e - i * n;
+            if (j > i || !(d[i] > -DBL_MAX) || !(d[j] > -DBL_MAX)) continue;
+            double s = Aat(i, j);
+            for (int t = 0; t < r; t++) s = fma(-G[(size_t)t * ldg + i], G[(size_t)t * ldg + j], s);
+            if (!(fabs(s) <= 1e-10 * dmax0)) bad = true;
+        }
+        if (bad) S.flags[2] = 1;
+        __syncthreads();
+        if (S.flags[2]) return -1;
+    }
+    if (r == 0) {                                      // A = 0: the minimum-norm solution is 0
+        for (int i = tid; i < n; i += T) xout[i] = 0.0;
+        __syncthreads();
+        return 0;
+    }
+
+    VH_T(0);
+    // ---------------- one-sided Jacobi on the r columns ----------------
+    const int m = (r + 1) & ~1, NP = m >> 1;
+    constexpr int PG = T / LP;
+    const int pg = tid / LP, pl = tid % LP;
+    const int nchunk = (n + 1) >> 1;                   // 16-byte chunks per column (rows beyond n are zero)
+    const double negl = 1e-2 * DBL_EPSILON * (double)n * dmax0;   // both columns below: dropped whatever they mix into
+    const double tol2 = DBL_EPSILON * DBL_EPSILON;               // rotate when cos^2 > tol2
+    const double thr2 = 1e-14;                                    // another sweep when some cos^2 > thr2 (cos 1e-7: the
+                                                                  // sweep leaves cos^2 ~ 1e-28 behind, quadratic convergence)
+    int sweep = 0;
+    if (r > 1) {
+        // the tournament's pairs, once per solve: tab[step * NP + k] = p | q << 8 (q = 255: padding of an odd r)
+        unsigned short* tab = S.tab;
+        for (int e = tid; e < (m - 1) * NP; e += T) {
+            int p, q;
+            vh_rr_pair(e % NP, e / NP, m, p, q);
+            tab[e] = (unsigned short)(p | ((q < r ? q : 255) << 8));
+        }
+        if (tid == 0) { S.flags[0] = 0; S.flags[1] = 0; }
+        __syncthreads();
+        for (; sweep < 30; sweep++) {
+            if (tid == 0) S.flags[(sweep + 1) & 1] = 0;
+            for (int step = 0; step < m - 1; step++) {
+                for (int k0 = 0; k0 < NP; k0 += PG) {
+                    const int k = k0 + pg;
+                    int p = 0, q = 255;
+                    if (k < NP) { const unsigned pq = tab[step * NP + k]; p = pq & 255; q = pq >> 8; }
+                    const bool valid = q != 255;
+                    VH_T(1);
+                    double2 xp[UMAX], xq[UMAX];
+                    double2* cp = reinterpret_cast<double2*>(G + (size_t)p * ldg);
+                    double2* cq = reinterpret_cast<double2*>(G + (size_t)(valid ? q : 0) * ldg);
+#pragma unroll
+                    for (int u = 0; u < UMAX; u++) {
+                        const int c = pl + LP * u;
+                        if (valid && c < nchunk) { xp[u] = cp[c]; xq[u] = cq[c]; }
+                        else { xp[u] = make_double2(0.0, 0.0); xq[u] = make_double2(0.0, 0.0); }
+                    }
+                    double al0 = 0.0, be0 = 0.0, ga0 = 0.0, al1 = 0.0, be1 = 0.0, ga1 = 0.0;      // two chains per sum
+#pragma unroll
+                    for (int u = 0; u < UMAX; u++) {
+                        al0 = fma(xp[u].x, xp[u].x, al0); al1 = fma(xp[u].y, xp[u].y, al1);
+                        be0 = fma(xq[u].x, xq[u].x, be0); be1 = fma(xq[u].y, xq[u].y, be1);
+                        ga0 = fma(xp[u].x, xq[u].x, ga0); ga1 = fma(xp[u].y, xq[u].y, ga1);
+                    }
+                    double al = al0 + al1, be = be0 + be1, ga = ga0 + ga1;
+                    VH_T(2);
+#pragma unroll
+                    for (int o = LP >> 1; o > 0; o >>= 1) {
+                        al += __shfl_xor_sync(full, al, o);
+                        be += __shfl_xor_sync(full, be, o);
+                        ga += __shfl_xor_sync(full, ga, o);
+                    }
+                    VH_T(3);
+                    if (!valid || (al <= negl && be <= negl)) continue;       // no shuffles below this line
+                    const double g2 = ga * ga, ab = al * be;
+                    if (g2 > thr2 * ab && pl == 0) S.flags[sweep & 1] = 1;
+                    if (g2 > tol2 * ab) {
+                        // Jacobi rotation that orthogonalises the two columns, with w = be - al, g = 2 ga, hyp = sqrt(w^2 + g^2):
+                        //   tan = sign(w) g / (|w| + hyp),  cos^2 = (|w| + hyp) / (2 hyp),  sin = sign(w) g / (2 hyp cos)
+                        // — two reciprocal square roots and no division on the dependent chain.  w and g are first scaled by
+                        // a power of two near 1 / max(al, be), so that the squares neither overflow nor vanish.
+                        const int ex = (__double2hiint(fmax(al, be)) >> 20) & 0x7ff;
+                        const double scale = __hiloint2double((2046 - ex) << 20, 0);      // 2^(1023 - ex)
+                        const double w = (be - al) * scale, g = 2.0 * ga * scale;
+                        const double qq = fma(w, w, g * g);
+                        const double rs = vh_rsqrt(qq);
+                        const double hyp = qq * rs;
+                        const double den = fabs(w) + hyp;
+                        const double u2 = 0.5 * den * rs;                     // cos^2 in [1/2, 1]
+                        const double rc = vh_rsqrt(u2);
+                        const double c = u2 * rc;
+                        const double s = copysign(0.5 * g * rs, g * w) * rc;  // sign(w) g: w = 0 counts as positive
+                        VH_T(4);
+#pragma unroll
+                        for (int u = 0; u < UMAX; u++) {
+                            const int cidx = pl + LP * u;
+                            if (cidx < nchunk) {
+                                const double2 a = xp[u], b = xq[u];
+                                cp[cidx] = make_double2(fma(c, a.x, -s * b.x), fma(c, a.y, -s * b.y));
+                                cq[cidx] = make_double2(fma(s, a.x, c * b.x), fma(s, a.y, c * b.y));
+                            }
+                        }
+                        VH_T(5);
+                    }
+                }
+                __syncthreads();
+                VH_T(6);
+            }
+            const int need = S.flags[sweep & 1];
+            __syncthreads();                           // the flag is cleared again at the start of the next sweep
+            if (!need) { sweep++; break; }
+        }
+    }
+    if (sweeps_out && tid == 0) *sweeps_out = sweep;
+
+    // ---------------- eigenvalues, truncation, minimum-norm sum ----------------
+    for (int i0 = 0; i0 < r; i0 += PG) {
+        const int i = i0 + pg;
+        const bool valid = i < r;
+        const double2* ci = reinterpret_cast<const double2*>(G + (size_t)(valid ? i : 0) * ldg);
+        double ss = 0.0, pb = 0.0;
+#pragma unroll
+        for (int u = 0; u < UMAX; u++) {
+            const int c = pl + LP * u;
+            if (valid && c < nchunk) {
+                const double2 g = ci[c];
+                const double b0 = bvec[2 * c], b1 = (2 * c + 1 < n) ? bvec[2 * c + 1] : 0.0;
+                ss = fma(g.x, g.x, ss); ss = fma(g.y, g.y, ss);
+                pb = fma(g.x, b0, pb); pb = fma(g.y, b1, pb);
+            }
+        }
+#pragma unroll
+        for (int o = LP >> 1; o > 0; o >>= 1) { ss += __shfl_xor_sync(full, ss, o); pb += __shfl_xor_sync(full, pb, o); }
+        if (valid && pl == 0) { S.lam[i] = ss; S.coef[i] = pb; }
+    }
+    __syncthreads();
+    double lmax = 0.0;
+    for (int i = lane; i < r; i += 32) lmax = fmax(lmax, S.lam[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(full, lmax, o));
+    const double cutoff = DBL_EPSILON * (double)n * lmax;
+    int rank = 0;
+    for (int i = lane; i < r; i += 32) rank += (S.lam[i] > cutoff) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(full, rank, o);
+    __syncthreads();
+    for (int i = tid; i < r; i += T) {
+        const double l = S.lam[i];
+        S.coef[i] = (l > cutoff) ? S.coef[i] / (l * l) : 0.0;
+    }
+    __syncthreads();
+    for (int i0 = warp * RPW; i0 < n; i0 += nwarps * RPW) {
+        const int i = i0 + rowlocal;
+        double acc = 0.0;
+        if (i < n)
+            for (int t = sub; t < r; t += TPR) acc = fma(G[(size_t)t * ldg + i], S.coef[t], acc);
+#pragma unroll
+        for (int o = RPW; o < 32; o <<= 1) acc += __shfl_xor_sync(full, acc, o);
+        if (sub == 0 && i < n) xout[i] = acc;
+    }
+    __syncthreads();
+    return rank;
+}
+
+}  // namespace bsde

@@ -11,6 +11,8 @@ data already on the GPU (then `result` may be a CUDA tensor too and nothing cros
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 
 from bsde_solver import xp
@@ -22,6 +24,12 @@ from bsde_solver.core.tensor.tensor_network import TensorNetwork  # noqa: F401
 from bsde_solver.core.tensor.tensor_train import TensorTrain, left_unfold, pack_cores, right_unfold, unpack_cores  # noqa: F401
 
 last_fit_info = {}
+RANK_LIMIT = 8      # largest bond rank of the fused CUDA kernels (csrc/api.cu: kRankLimit)
+
+
+class RankLimitWarning(RuntimeWarning):
+    """SALSA wanted to grow a bond beyond RANK_LIMIT; set warnings.simplefilter("error", RankLimitWarning) to make it fatal."""
+
 
 
 def _shape_of(phis):
@@ -75,5 +83,11 @@ def SALSA(phis, result, n_iter=10, ranks=None, omega=1.0, freq_omega=1.05, min_s
     y = result if _is_device_tensor(result) else be.to_device(np.asarray(result, dtype=np.float64).ravel())
     ranks_io = np.array(cur_ranks, dtype=np.int32)
     state = be.fit_salsa(inp, y, n_iter, ranks_io, init_ranks, omega, freq_omega, min_sv, max_rank, sid, do_reg, buf)
-    last_fit_info.update(eta=float(state[0]), omega=float(state[1]), min_sv=float(state[2]))
+    last_fit_info.update(eta=float(state[0]), omega=float(state[1]), min_sv=float(state[2]), rank_limited=bool(state[3]),
+                         cholesky=int(state[4]), jacobi=int(state[5]), lu=int(state[6]))
+    if state[3]:
+        # the reference would have grown a bond beyond what the CUDA kernels hold (als.py:122-123, :249-253): the fit
+        # that comes back is a valid SALSA fit with that bond capped, but NOT the reference's rank trajectory
+        warnings.warn(f"SALSA: rank growth stopped at the CUDA backend's limit of {RANK_LIMIT} (max_rank={max_rank} allows "
+                      f"more); ranks now {list(map(int, ranks_io))}", RankLimitWarning, stacklevel=2)
     return unpack_cores(tt, ranks_io, buf)

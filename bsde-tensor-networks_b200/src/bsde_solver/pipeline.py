@@ -39,6 +39,13 @@ def simulate_paths(model, X0, n_steps, batch_size, paths="philox", seed=0, sampl
     raise ValueError(f"unknown paths mode {paths}")
 
 
+def _is_salsa(optimizer):
+    """True for SALSA itself and for functools.partial wrappers around it (any depth)."""
+    while isinstance(optimizer, partial):
+        optimizer = optimizer.func
+    return optimizer is SALSA
+
+
 def _mean(v):
     """Mean over all samples of all ranks (sample-sharded runs combine the per-rank sums)."""
     from bsde_solver._backend import get_backend
@@ -107,7 +114,9 @@ def run_implicit(model, basis, X, xi, n_iter, n_iter_implicit, ranks, optimizer=
         t0 = time.perf_counter()
         inp = basis.device_inputs(X[n])
         Y_nk = Y[n + 1]
-        opt = partial(optimizer, do_reg=False) if (n == 0 and no_reg_at_0 and optimizer is SALSA) else optimizer
+        # the reference passes do_reg=False at n == 0 whenever the optimiser is SALSA (pipeline_explicit.py:103-104,
+        # experiments/n_assets.py:176-179) — also when it arrives wrapped in functools.partial(SALSA, max_rank=...)
+        opt = partial(optimizer, do_reg=False) if (n == 0 and no_reg_at_0 and _is_salsa(optimizer)) else optimizer
         for _ in range(n_iter_implicit):
             grad = multi_derivative(V, inp)
             target = be.target(model.model_id, model.params(), X[n], Y_nk, Y[n + 1], grad, xi[n + 1], dt, True)
