@@ -13,7 +13,15 @@ own 2^20 samples (weak scaling) and the per-core normal equations are all-reduce
 Printed JSON line (rank 0): `value` = whole-job samples·sweeps/s with inputs resident in HBM; `e2e` = the same
 through the host-buffer entry point (bsde_fit_als_host: pinned host X and y copied in, cores copied out, inside
 the timed region); `roofline` = the assembly kernel against the FP64 tensor-pipe peak; `cpu_baseline` = the numpy
-oracle port on this host's cores on a bounded sample.  `--impl reference` times that CPU port alone.
+oracle port on this host's cores on a bounded sample.  Further keys of the same line, so that BENCH / SCALE alone say
+what a fit that actually fits costs: `converging` = the same kernel shape on a target the train can
+represent (Black-Scholes law, y = |x|^2: the fit converges and most solves are rank-deficient, i.e. take the truncated
+path); `full_solve` = seconds and Y0 against the analytic price of the largest explicit backward solve that converges
+(Black-Scholes d = 20, N = 2^20, 50 steps, rank 4, 4 monomials; strong scaling over the GPUs); `e2e_phis` = the reference's
+own calling convention ALS(phis, y) with host lists of (N, p) arrays; `multi_gpu_check` (N > 1) = replicas bit-identical
+and the sharded fit against the single-GPU fit of the union.
+`--impl reference` times the UNMODIFIED reference (pip-installed into baseline/_ref, run on oracle/shim's stand-in for the
+absent opt_einsum) on a bounded sample whose true size is in `config`, with the oracle port beside it.
 """
 import argparse
 import json
@@ -137,27 +145,48 @@ def host_threads():
     return os.cpu_count() or 1
 
 
+REF_SAMPLE_N, REF_SWEEPS = 1 << 10, 1       # unmodified reference: 2^10 samples, one sweep per step (~5 s per step on 8 cores)
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path (oracle port; the Python reference itself cannot travel
-    to the GPU box) on this host's cores, one bounded fit per step."""
+    """--impl reference: the reference's own CPU implementation of the path on this host's cores, one bounded fit per step.
+    The unmodified reference (baseline/_ref + oracle/shim) when it is installed, else the numpy oracle port."""
     if rank != 0:
         return
-    for _ in range(args.warmup):
-        cpu_port(CPU_SAMPLE_N, N_SWEEPS)
-    t = 0.0
-    for _ in range(args.steps):
-        t += cpu_port(CPU_SAMPLE_N, N_SWEEPS)
-    value = CPU_SAMPLE_N * N_SWEEPS * args.steps / t
-    sample = f"ALS fit, d={D} r={R} p={P}, N=2^{int(np.log2(CPU_SAMPLE_N))} samples, {N_SWEEPS} sweeps per step (numpy oracle port, cached interfaces)"
-    print(json.dumps({
-        "impl": "reference", "metric": "samples*sweeps/s (TT regression, ALS)", "value": value, "unit": "samples*sweeps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(world),
-        "cpu_baseline": {"value": value, "unit": "samples*sweeps/s", "cores": host_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "samples*sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
+    import oracle.run_reference as RR
+
+    port = {}
+    for n in (1 << 12, 1 << 14):
+        t = cpu_port(n, 2)
+        port[f"N=2^{int(np.log2(n))}"] = n * 2 / t
+    common = {"impl": "reference", "metric": "samples*sweeps/s (TT regression, ALS)", "unit": "samples*sweeps/s", "n_gpus": args.gpus,
+              "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+              "data": "synthetic", "gpu_launches": 0}
+    if RR.available():
+        times = RR.time_als(D, REF_SAMPLE_N, R, P, REF_SWEEPS, args.steps, args.warmup)
+        t = float(sum(times))
+        value = REF_SAMPLE_N * REF_SWEEPS * args.steps / t
+        sample = (f"UNMODIFIED reference ALS (baseline/_ref, bsde_solver.core.optimisation.als.ALS on oracle/shim's opt_einsum stand-in), "
+                  f"d={D} r={R} p={P}, N=2^{int(np.log2(REF_SAMPLE_N))} samples (NOT 2^20: the reference recomputes every interface per "
+                  f"micro-step and cannot allocate the full batch), {REF_SWEEPS} sweep per step")
+        kind, n_ref, sw_ref = "reference", REF_SAMPLE_N, REF_SWEEPS
+    else:
+        t = 0.0
+        for _ in range(args.warmup):
+            cpu_port(CPU_SAMPLE_N, N_SWEEPS)
+        for _ in range(args.steps):
+            t += cpu_port(CPU_SAMPLE_N, N_SWEEPS)
+        value = CPU_SAMPLE_N * N_SWEEPS * args.steps / t
+        sample = f"numpy oracle port (cached interfaces; baseline/_ref is not installed), d={D} r={R} p={P}, N=2^{int(np.log2(CPU_SAMPLE_N))} samples, {N_SWEEPS} sweeps per step"
+        kind, n_ref, sw_ref = "port", CPU_SAMPLE_N, N_SWEEPS
+    cfg = dict(workload_config(world), samples_per_gpu=n_ref, global_samples=n_ref, sweeps_per_step=sw_ref,
+               workload=f"C3 ALS fit shape (HJB law, d={D}, rank {R}, {P} monomials/asset) on a BOUNDED sample of N=2^{int(np.log2(n_ref))} samples, {sw_ref} sweep(s) per step, host CPU",
+               l2="n/a (CPU)", parallelism="host threads (BLAS)")
+    print(json.dumps(dict(common, value=value, ms_per_step=1e3 * t / args.steps, config=cfg,
+                          cpu_baseline={"value": value, "unit": "samples*sweeps/s", "cores": host_threads(), "kind": kind, "sample": sample,
+                                        "oracle_port_samples_sweeps_per_s": port,
+                                        "note": "the port caches the interfaces (O(d) per sweep); the reference recontracts them per micro-step (O(d^2))"},
+                          e2e={"value": value, "unit": "samples*sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})))
 
 
 def workload_config(world):

@@ -41,13 +41,13 @@ def hjb_reference_price(be, d, sigma, T, n_draws=1 << 22, seed=99):
     return -np.log(acc / cnt)
 
 
-def run(samples=1 << 20, assets=100, steps=50, rank=4, degree=4, sweeps=10, seed=0, verbose=False):
+def run(samples=1 << 20, assets=100, steps=50, rank=4, degree=4, sweeps=10, seed=0, verbose=False, model_name="hjb"):
     import torch
     import torch.distributed as dist
 
     from bsde_solver._backend import get_backend
     from bsde_solver._shard import shard_range
-    from bsde_solver.bsde import HJB
+    from bsde_solver.bsde import HJB, BlackScholes
     from bsde_solver.core.calculus.basis import PolynomialBasis
     from bsde_solver.core.optimisation.als import ALS
     from bsde_solver.pipeline import predicted_price, run_explicit, simulate_paths
@@ -56,9 +56,15 @@ def run(samples=1 << 20, assets=100, steps=50, rank=4, degree=4, sweeps=10, seed
     rk = dist.get_rank() if dist.is_initialized() else 0
     be = get_backend()
     np.random.seed(seed)                          # initial cores come from the global numpy stream (als.py:37): same on every rank
-    T, sigma = 1.0, float(np.sqrt(2.0))
-    X0 = np.zeros(assets)
-    model = HJB(np.tile(X0, (1, 1)), T / steps, T, sigma=sigma)
+    T = 1.0
+    if model_name == "hjb":                       # BASELINE.json configs[2]: X0 = 0, sigma = sqrt(2)   (pipeline_explicit.py:33)
+        sigma = float(np.sqrt(2.0))
+        X0 = np.zeros(assets)
+        model = HJB(np.tile(X0, (1, 1)), T / steps, T, sigma=sigma)
+    else:                                         # the reference's Black-Scholes literals: X0 = (1, 0.5, ...), sigma = 0.4, r = 0.05
+        sigma, rate = 0.4, 0.05                   # (src/scripts/pipeline.py:52-59)
+        X0 = np.tile([1.0, 0.5], (assets + 1) // 2)[:assets]
+        model = BlackScholes(np.tile(X0, (1, 1)), T / steps, T, rate, sigma)
     basis = PolynomialBasis(degree)
     ranks = (1,) + (rank,) * (assets - 1) + (1,)
     lo, hi = shard_range(samples, rk, world)
@@ -88,12 +94,16 @@ def run(samples=1 << 20, assets=100, steps=50, rank=4, degree=4, sweeps=10, seed
     y0 = predicted_price(Y)
     out = None
     if rk == 0:
-        ref = hjb_reference_price(be, assets, sigma, T)
+        if model_name == "hjb":
+            ref, ref_kind = hjb_reference_price(be, assets, sigma, T), "Monte-Carlo closed form, 2^22 draws (bsde.py:98-102)"
+        else:
+            ref, ref_kind = float(np.exp((rate + sigma**2) * T) * np.sum(X0**2)), "analytic exp((r + sigma^2) T) |X0|^2 (bsde.py:54-55)"
         fits = steps + 1
-        out = {"workload": f"full explicit BSDE solve: HJB d={assets}, N={samples} paths, {steps} steps, rank {rank}, {degree} monomials/asset, ALS {sweeps} sweeps/fit, {fits} fits",
+        out = {"workload": f"full explicit BSDE solve: {'HJB' if model_name == 'hjb' else 'Black-Scholes'} d={assets}, N={samples} paths, {steps} steps, rank {rank}, {degree} monomials/asset, ALS {sweeps} sweeps/fit, {fits} fits",
                "n_gpus": world, "scaling": "strong (N split over the GPUs)", "paths_s": t_paths, "solve_s": t_solve, "total_s": t_paths + t_solve,
                "wall_s_host_clock": wall, "samples_sweeps_per_s": samples * sweeps * fits / t_solve,
-               "Y0": y0, "Y0_reference_mc": ref, "Y0_rel_err": abs(y0 - ref) / abs(ref),
+               "Y0": y0, "Y0_reference": ref, "Y0_reference_kind": ref_kind, "Y0_rel_err": abs(y0 - ref) / abs(ref),
+               "step_time_s_min_median_max": [float(np.min(step_times)), float(np.median(step_times)), float(np.max(step_times))],
                "paths_bytes_per_gpu": int(X.numel() * 8), "dtype": "f64"}
     del X, Y
     return out
@@ -109,6 +119,7 @@ def main():
     ap.add_argument("--sweeps", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--model", default="hjb", choices=["hjb", "bs"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -122,7 +133,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         get_backend().init_distributed()
-    out = run(args.samples, args.assets, args.steps, args.rank, args.degree, args.sweeps, args.seed, args.verbose)
+    out = run(args.samples, args.assets, args.steps, args.rank, args.degree, args.sweeps, args.seed, args.verbose, args.model)
     if out is not None:
         print(json.dumps(out))
     if world > 1:

@@ -925,15 +925,19 @@ int bsde_fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const dou
     return fit_als(c, basis_kind, d, p, N, inputs_dev, coef_host, y_dev, n_iter, ranks, solver_id, cores_host, info_host);
 }
 
-int bsde_fit_als_host(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_host,
-                      const double* coef_host, const double* y_host, int n_iter, const int* ranks, int solver_id,
-                      double* cores_host, int* info_host) {
-    BSDE_CHECK_CTX(c);
-    Guard g(c);
-    if (!inputs_host || !y_host) return fail_msg(2, "fit_als_host: null input pointer");
+// Host-buffer fits: asset j's block (N values of x_j, or its p basis rows [p][N]) is read from asset_ptrs[j].  The blocks
+// arrive asset by asset on a copy stream in the order the right interfaces are built (d-1 .. 1, then asset 0 and y), so
+// that build_right overlaps the tail of the transfer.
+static int fit_als_host_blocks(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* const* asset_ptrs,
+                               const double* coef_host, const double* y_host, int n_iter, const int* ranks, int solver_id,
+                               double* cores_host, int* info_host) {
+    if (!asset_ptrs || !y_host) return fail_msg(2, "fit_als_host: null input pointer");
     if (N < 1 || d < 1 || p < 1) return fail_msg(2, "fit_als_host: bad sizes");
-    const size_t in_bytes = sizeof(double) * (size_t)d * (basis_kind == BSDE_BASIS_PHI ? p : 1) * (size_t)N;
-    BSDE_TRY(c->in_copy.ensure(in_bytes));
+    if (basis_kind < 0 || basis_kind > 2) return fail_msg(2, "unknown basis_kind %d", basis_kind);
+    for (int j = 0; j < d; j++)
+        if (!asset_ptrs[j]) return fail_msg(2, "fit_als_host: asset %d has a null block", j);
+    const size_t chunk = sizeof(double) * (size_t)(basis_kind == BSDE_BASIS_PHI ? p : 1) * (size_t)N;   // one asset
+    BSDE_TRY(c->in_copy.ensure(chunk * (size_t)d));
     BSDE_TRY(c->y_copy.ensure(sizeof(double) * (size_t)N));
     if (d >= 2 && c->world == 1) {
         if (!c->copy_stream) BSDE_CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -945,17 +949,16 @@ int bsde_fit_als_host(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, cons
         // the copy stream starts after whatever the context's stream still does with the staging buffers
         BSDE_CUDA_OK(cudaEventRecord(c->in_ev[d + 1], c->stream));
         BSDE_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->in_ev[d + 1], 0));
-        const size_t chunk = in_bytes / (size_t)d;                       // one asset: N values, or its p basis rows
         for (int j = d - 1; j >= 0; j--) {
-            BSDE_CUDA_OK(cudaMemcpyAsync((char*)c->in_copy.p + (size_t)j * chunk, (const char*)inputs_host + (size_t)j * chunk, chunk,
-                                         cudaMemcpyHostToDevice, c->copy_stream));
+            BSDE_CUDA_OK(cudaMemcpyAsync((char*)c->in_copy.p + (size_t)j * chunk, asset_ptrs[j], chunk, cudaMemcpyHostToDevice, c->copy_stream));
             BSDE_CUDA_OK(cudaEventRecord(c->in_ev[j], c->copy_stream));
         }
         BSDE_CUDA_OK(cudaMemcpyAsync(c->y_copy.p, y_host, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->copy_stream));
         BSDE_CUDA_OK(cudaEventRecord(c->in_ev[d], c->copy_stream));
         c->in_ev_count = d + 1;
     } else {
-        BSDE_CUDA_OK(cudaMemcpyAsync(c->in_copy.p, inputs_host, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        for (int j = 0; j < d; j++)
+            BSDE_CUDA_OK(cudaMemcpyAsync((char*)c->in_copy.p + (size_t)j * chunk, asset_ptrs[j], chunk, cudaMemcpyHostToDevice, c->stream));
         BSDE_CUDA_OK(cudaMemcpyAsync(c->y_copy.p, y_host, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
     }
     const int rc = fit_als(c, basis_kind, d, p, N, c->in_copy.as<double>(), coef_host, c->y_copy.as<double>(), n_iter, ranks, solver_id,
@@ -965,6 +968,27 @@ int bsde_fit_als_host(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, cons
         c->in_ev_count = 0;
     }
     return rc;
+}
+
+int bsde_fit_als_host(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_host,
+                      const double* coef_host, const double* y_host, int n_iter, const int* ranks, int solver_id,
+                      double* cores_host, int* info_host) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (!inputs_host) return fail_msg(2, "fit_als_host: null input pointer");
+    if (N < 1 || d < 1 || p < 1) return fail_msg(2, "fit_als_host: bad sizes");
+    const size_t chunk = (size_t)(basis_kind == BSDE_BASIS_PHI ? p : 1) * (size_t)N;
+    std::vector<const double*> ptrs((size_t)d);
+    for (int j = 0; j < d; j++) ptrs[j] = inputs_host + (size_t)j * chunk;
+    return fit_als_host_blocks(c, basis_kind, d, p, N, ptrs.data(), coef_host, y_host, n_iter, ranks, solver_id, cores_host, info_host);
+}
+
+int bsde_fit_als_host_assets(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* const* asset_ptrs_host,
+                             const double* coef_host, const double* y_host, int n_iter, const int* ranks, int solver_id,
+                             double* cores_host, int* info_host) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    return fit_als_host_blocks(c, basis_kind, d, p, N, asset_ptrs_host, coef_host, y_host, n_iter, ranks, solver_id, cores_host, info_host);
 }
 
 int bsde_fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* coef_host,
@@ -1154,6 +1178,80 @@ int bsde_orthonormalize(bsde_ctx* c, int d, int p, const int* ranks, double* cor
     else BSDE_TRY(launch_orthonormalize_left(T.cores, T.off_dev, T.ranks_dev, p, d, start, stop, c->stream));
     c->launches++;
     BSDE_TRY(train_download(c, T, cores_host));
+    return 0;
+}
+
+int bsde_salsa_move(bsde_ctx* c, int side, int ra, int p, int k, int rb, double min_sv, int expand, int do_reg,
+                    double* core_a_host, double* core_b_host, double* reg_out_host, int* rank_out, int* adapted_out) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (side != 0 && side != 1) return fail_msg(2, "salsa_move: side must be 0 (left move) or 1 (right move)");
+    if (!core_a_host || !core_b_host) return fail_msg(2, "salsa_move: null core pointer");
+    if (ra < 1 || p < 1 || p > kMaxP || k < 1 || k > 8 || rb < 1 || ra > 8 || rb > 8) return fail_msg(2, "salsa_move: shape (%d,%d,%d)-(%d) outside the kernels' range", ra, p, k, rb);
+    if (side == 0 && expand && k >= 8) return fail_msg(2, "salsa_move: bond rank %d cannot grow beyond 8", k);
+    const int kcap = k + 1;                                   // room for one more rank
+    const size_t na = (size_t)ra * p * kcap, nb = (size_t)kcap * p * rb;
+    BSDE_TRY(c->dbg.ensure(sizeof(double) * (na + nb + 16 + 2) + 64));
+    double* a_dev = c->dbg.as<double>();
+    double* b_dev = a_dev + na;
+    double* reg_dev = b_dev + nb;                             // gamma / theta: up to 9 values
+    double* msv_dev = reg_dev + 12;
+    int* flags_dev = (int*)(msv_dev + 2);                     // [0] adapted, [1] rank
+    BSDE_CUDA_OK(cudaMemsetAsync(a_dev, 0, sizeof(double) * (na + nb + 16 + 2) + 64, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(a_dev, core_a_host, sizeof(double) * (size_t)ra * p * k, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(b_dev, core_b_host, sizeof(double) * (size_t)k * p * rb, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(msv_dev, &min_sv, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int init_flags[2] = {0, k};
+    BSDE_CUDA_OK(cudaMemcpyAsync(flags_dev, init_flags, sizeof init_flags, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (side == 0) BSDE_TRY(launch_salsa_left(a_dev, b_dev, ra, p, k, rb, msv_dev, expand ? 1 : 0, do_reg ? 1 : 0, reg_dev, flags_dev + 1, flags_dev, c->stream));
+    else BSDE_TRY(launch_salsa_right(a_dev, b_dev, ra, p, k, rb, msv_dev, do_reg ? 1 : 0, reg_dev, c->stream));
+    c->launches++;
+    int flags[2];
+    BSDE_CUDA_OK(cudaMemcpyAsync(flags, flags_dev, sizeof flags, cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    const int knew = (side == 0 && flags[0]) ? flags[1] : k;
+    if (knew < k || knew > kcap) return fail_msg(3, "salsa_move: kernel reported bond rank %d", knew);
+    BSDE_CUDA_OK(cudaMemcpyAsync(core_a_host, a_dev, sizeof(double) * (size_t)ra * p * knew, cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(core_b_host, b_dev, sizeof(double) * (size_t)knew * p * rb, cudaMemcpyDeviceToHost, c->stream));
+    if (reg_out_host && do_reg) BSDE_CUDA_OK(cudaMemcpyAsync(reg_out_host, reg_dev, sizeof(double) * knew, cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (rank_out) *rank_out = knew;
+    if (adapted_out) *adapted_out = side == 0 ? flags[0] : 0;
+    return 0;
+}
+
+int bsde_orthonormalize_shape(bsde_ctx* c, int d, const int* shape, const int* ranks, double* cores_host, int mode, int start, int stop) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    if (!shape || !cores_host) return fail_msg(2, "orthonormalize: null pointer");
+    int pmax = 1;
+    for (int j = 0; j < d; j++) {
+        if (shape[j] < 1 || shape[j] > kMaxP) return fail_msg(2, "basis size shape[%d] = %d outside 1..%d", j, shape[j], kMaxP);
+        pmax = std::max(pmax, shape[j]);
+    }
+    BSDE_TRY(check_ranks(d, pmax, ranks));
+    if (mode != 0 && mode != 1) return fail_msg(2, "orthogonality must be either 'left' or 'right'");
+    if (stop == -1) stop = d - 1;
+    if (start < 0 || stop > d - 1) return fail_msg(2, "orthonormalize: range %d..%d outside the train", start, stop);
+    // cores packed back to back with their own basis sizes: offsets, ranks and shape go to the device next to them
+    std::vector<int64_t> off((size_t)d);
+    int64_t total = 0;
+    for (int j = 0; j < d; j++) { off[j] = total; total += (int64_t)ranks[j] * shape[j] * ranks[j + 1]; }
+    BSDE_TRY(c->cores.ensure(sizeof(double) * (size_t)total));
+    BSDE_TRY(c->meta.ensure(sizeof(int64_t) * d + sizeof(int) * (2 * d + 1) + 64));
+    int64_t* off_dev = c->meta.as<int64_t>();
+    int* ranks_dev = (int*)(off_dev + d);
+    int* shape_dev = ranks_dev + d + 1;
+    BSDE_CUDA_OK(cudaMemcpyAsync(off_dev, off.data(), sizeof(int64_t) * d, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(ranks_dev, ranks, sizeof(int) * (d + 1), cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(shape_dev, shape, sizeof(int) * d, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaMemcpyAsync(c->cores.p, cores_host, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, c->stream));
+    if (mode == 1) BSDE_TRY(launch_orthonormalize_right(c->cores.as<double>(), off_dev, ranks_dev, pmax, d, start, stop, c->stream, shape_dev));
+    else BSDE_TRY(launch_orthonormalize_left(c->cores.as<double>(), off_dev, ranks_dev, pmax, d, start, stop, c->stream, shape_dev));
+    c->launches++;
+    BSDE_CUDA_OK(cudaMemcpyAsync(cores_host, c->cores.p, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -1389,6 +1389,7 @@ struct OrthoArgs {
     double* cores;
     const int64_t* off;   // device
     const int* ranks;     // device
+    const int* pvec;      // device, d basis sizes — or null: every core has p
     int p, d, start, stop, right;
 };
 
@@ -1400,19 +1401,19 @@ k_orthonormalize(OrthoArgs a) {
     double* qrR = W + kMaxR * kMaxP * kMaxR;
     double* tau = qrR + kMaxR * kMaxR;
     double* vbuf = tau + kMaxR;
-    const int p = a.p;
     if (a.right) {
         for (int k = a.stop; k > a.start; k--) {
             double* cur = a.cores + a.off[k];
             double* prev = a.cores + a.off[k - 1];
             const int rl = a.ranks[k], rr = a.ranks[k + 1], rp = a.ranks[k - 1];
+            const int p = a.pvec ? a.pvec[k] : a.p, pprev = a.pvec ? a.pvec[k - 1] : a.p;
             const int mrows = p * rr, kk = rl, n = rl * p * rr;
             for (int e = threadIdx.x; e < n; e += blockDim.x) { const int r = e / kk, c = e % kk; Mq[e] = cur[c * mrows + r]; }
             __syncthreads();
             if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, kk, kk, qrR, tau, vbuf);
             __syncthreads();
             for (int e = threadIdx.x; e < n; e += blockDim.x) { const int c = e / mrows, r = e % mrows; cur[e] = Mq[r * kk + c]; }
-            const int rows = rp * p;
+            const int rows = rp * pprev;
             for (int e = threadIdx.x; e < rows * kk; e += blockDim.x) {
                 const int r = e / kk, c = e % kk;
                 double acc = 0.0;
@@ -1428,13 +1429,14 @@ k_orthonormalize(OrthoArgs a) {
             double* cur = a.cores + a.off[k];
             double* next = a.cores + a.off[k + 1];
             const int rl = a.ranks[k], rr = a.ranks[k + 1], rn = a.ranks[k + 2];
+            const int p = a.pvec ? a.pvec[k] : a.p, pnext = a.pvec ? a.pvec[k + 1] : a.p;
             const int mrows = rl * p, kk = rr, n = rl * p * rr;
             for (int e = threadIdx.x; e < n; e += blockDim.x) Mq[e] = cur[e];
             __syncthreads();
             if (threadIdx.x < 32) warp_householder_qr(Mq, mrows, kk, kk, qrR, tau, vbuf);
             __syncthreads();
             for (int e = threadIdx.x; e < n; e += blockDim.x) cur[e] = Mq[e];
-            const int cols = p * rn;
+            const int cols = pnext * rn;
             for (int e = threadIdx.x; e < kk * cols; e += blockDim.x) {
                 const int r = e / cols, c = e % cols;
                 double acc = 0.0;
@@ -1495,8 +1497,8 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_laun
 }
 
 static int launch_ortho(double* cores, const int64_t* off_dev, const int* ranks_dev, int p, int d, int start, int stop,
-                        int right, cudaStream_t st) {
-    OrthoArgs a{cores, off_dev, ranks_dev, p, d, start, stop, right};
+                        int right, cudaStream_t st, const int* pvec_dev = nullptr) {
+    OrthoArgs a{cores, off_dev, ranks_dev, pvec_dev, p, d, start, stop, right};
     const size_t bytes = sizeof(double) * (2 * kMaxR * kMaxP * kMaxR + kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16);
     k_orthonormalize<<<1, kDenseThreads, bytes, st>>>(a);
     BSDE_CUDA_OK(cudaGetLastError());
@@ -1504,12 +1506,12 @@ static int launch_ortho(double* cores, const int64_t* off_dev, const int* ranks_
 }
 
 int launch_orthonormalize_right(double* cores, const int64_t* off_dev, const int* ranks_dev, int p, int d, int start,
-                                int stop, cudaStream_t st) {
-    return launch_ortho(cores, off_dev, ranks_dev, p, d, start, stop, 1, st);
+                                int stop, cudaStream_t st, const int* pvec_dev) {
+    return launch_ortho(cores, off_dev, ranks_dev, p, d, start, stop, 1, st, pvec_dev);
 }
 int launch_orthonormalize_left(double* cores, const int64_t* off_dev, const int* ranks_dev, int p, int d, int start,
-                               int stop, cudaStream_t st) {
-    return launch_ortho(cores, off_dev, ranks_dev, p, d, start, stop, 0, st);
+                               int stop, cudaStream_t st, const int* pvec_dev) {
+    return launch_ortho(cores, off_dev, ranks_dev, p, d, start, stop, 0, st, pvec_dev);
 }
 
 }  // namespace bsde

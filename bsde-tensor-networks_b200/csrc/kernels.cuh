@@ -112,10 +112,11 @@ struct MicroSolveArgs {
 };
 // *extra_launches: kernels launched in front of k_micro_solve (the fast kernel, see dense.cu)
 int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_launches = nullptr);
-int launch_orthonormalize_right(double* cores, const int64_t* core_off_host, const int* ranks_host, int p, int d,
-                                int start, int stop, cudaStream_t st);
-int launch_orthonormalize_left(double* cores, const int64_t* core_off_host, const int* ranks_host, int p, int d,
-                               int start, int stop, cudaStream_t st);
+// pvec_dev: optional per-core basis sizes (device, d ints) for trains with a ragged `shape` (tensor_train.py:18-32)
+int launch_orthonormalize_right(double* cores, const int64_t* core_off_dev, const int* ranks_dev, int p, int d,
+                                int start, int stop, cudaStream_t st, const int* pvec_dev = nullptr);
+int launch_orthonormalize_left(double* cores, const int64_t* core_off_dev, const int* ranks_dev, int p, int d,
+                               int start, int stop, cudaStream_t st, const int* pvec_dev = nullptr);
 
 
 // ---- model.cu ------------------------------------------------------------------------------------

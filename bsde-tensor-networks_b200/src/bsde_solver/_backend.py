@@ -179,6 +179,18 @@ class Backend:
                                          _ptr(info))
         return info
 
+    def fit_als_host_assets(self, kind, p, blocks, coef, y_host, n_iter, ranks, solver_id, cores_flat):
+        """One contiguous host block per asset (N values of x_j, or its (p, N) basis rows), consumed where it lies."""
+        ranks = _i32(ranks)
+        info = np.zeros(4, dtype=np.int32)
+        coef = None if coef is None else _f64(coef)
+        d = len(blocks)
+        N = int(blocks[0].shape[-1])
+        ptrs = (C.c_void_p * d)(*[b.ctypes.data for b in blocks])
+        self._call(self.lib.bsde_fit_als_host_assets, int(kind), d, int(p), N, C.cast(ptrs, C.c_void_p), _ptr(coef),
+                                                _ptr(y_host), int(n_iter), _ptr(ranks), int(solver_id), _ptr(cores_flat), _ptr(info))
+        return info
+
     def fit_salsa(self, inp: DeviceInputs, y, n_iter, ranks, init_ranks, omega, freq_omega, min_sv, max_rank, solver_id,
                   do_reg, cores_buf):
         state = np.zeros(8, dtype=np.float64)
@@ -257,10 +269,33 @@ class Backend:
         return x, info
 
     def orthonormalize(self, p, ranks, cores_flat, mode, start, stop):
+        """p: one basis size for every core, or a sequence of per-core sizes (a ragged TensorTrain shape)."""
         ranks = _i32(ranks)
-        self._call(self.lib.bsde_orthonormalize, len(ranks) - 1, int(p), _ptr(ranks), _ptr(cores_flat), int(mode),
-                                           int(start), int(stop))
+        if np.ndim(p) == 0:
+            self._call(self.lib.bsde_orthonormalize, len(ranks) - 1, int(p), _ptr(ranks), _ptr(cores_flat), int(mode),
+                                               int(start), int(stop))
+        else:
+            shape = _i32(p)
+            if shape.shape[0] != len(ranks) - 1:
+                raise ValueError("one basis size per core expected")
+            self._call(self.lib.bsde_orthonormalize_shape, len(ranks) - 1, _ptr(shape), _ptr(ranks), _ptr(cores_flat), int(mode),
+                                                     int(start), int(stop))
         return cores_flat
+
+    def salsa_move(self, side, core_a, core_b, min_sv, expand=False, do_reg=True):
+        """One SVD move of SALSA on host cores (verification hook): returns (core_a, core_b, gamma_or_theta, adapted)."""
+        ra, p, k = core_a.shape
+        rb = core_b.shape[2]
+        a = np.zeros(ra * p * (k + 1))
+        b = np.zeros((k + 1) * p * rb)
+        a[: core_a.size] = _f64(core_a).ravel()
+        b[: core_b.size] = _f64(core_b).ravel()
+        reg = np.zeros(k + 2)
+        rank, adapted = C.c_int(), C.c_int()
+        self._call(self.lib.bsde_salsa_move, int(side), ra, p, k, rb, float(min_sv), int(bool(expand)), int(bool(do_reg)),
+                                       _ptr(a), _ptr(b), _ptr(reg), C.byref(rank), C.byref(adapted))
+        kn = rank.value
+        return (a[: ra * p * kn].reshape(ra, p, kn), b[: kn * p * rb].reshape(kn, p, rb), reg[:kn] if do_reg else None, bool(adapted.value))
 
     def basis_eval(self, kind, p, x, coef, deriv):
         N = int(x.numel())

@@ -30,6 +30,40 @@ def stack_phis(phis) -> np.ndarray:
     return out
 
 
+def asset_blocks(phis):
+    """The list as d contiguous (p, N) host blocks, without a stacked copy where the (N, p) arrays are F-ordered (the
+    reference's own layout, basis.py:21); anything else is copied asset by asset."""
+    phis = phis_list(phis)
+    blocks = []
+    for phi in phis:
+        a = np.asarray(phi).view(np.ndarray)
+        if a.ndim != 2:
+            raise ValueError("basis arrays must be (N, p)")
+        t = a.T
+        blocks.append(t if (t.flags["C_CONTIGUOUS"] and t.dtype == np.float64) else np.ascontiguousarray(t, dtype=np.float64))
+    if len({b.shape for b in blocks}) != 1:
+        raise ValueError("the CUDA backend needs the same number of samples and of basis functions for every asset")
+    return blocks
+
+
+def tagged_points(phis):
+    """(kind, p, coef, [x_j]) when every entry of the list is an untouched result of one of this package's basis objects
+    (same basis for all assets), else None."""
+    phis = phis_list(phis)
+    tags = [getattr(phi, "basis_tag", None) for phi in phis]
+    if not tags or any(t is None for t in tags):
+        return None
+    kind, p, coef, _ = tags[0]
+    for phi, t in zip(phis, tags):
+        if t[0] != kind or t[1] != p or np.shape(phi) != (t[3].shape[0], p):
+            return None
+        if (coef is None) != (t[2] is None) or (coef is not None and not np.array_equal(coef, t[2])):
+            return None
+    if len({t[3].shape[0] for t in tags}) != 1:
+        return None
+    return kind, p, coef, [t[3] for t in tags]
+
+
 def as_inputs(phis, dphis=None) -> DeviceInputs:
     """DeviceInputs are passed through; host lists are stacked and uploaded (explicit-values mode)."""
     if isinstance(phis, DeviceInputs):

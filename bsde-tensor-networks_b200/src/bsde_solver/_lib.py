@@ -42,6 +42,7 @@ SIGNATURES = {
     "bsde_transpose": [_vp, _vp, _i64, _i64, _vp],
     "bsde_fit_als": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp],
     "bsde_fit_als_host": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp],
+    "bsde_fit_als_host_assets": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp],
     "bsde_fit_salsa": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_double, C.c_double,
                        C.c_double, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp],
     "bsde_tt_eval": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp],
@@ -53,6 +54,8 @@ SIGNATURES = {
     "bsde_normal_eq": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp],
     "bsde_solve": [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp],
     "bsde_orthonormalize": [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int],
+    "bsde_salsa_move": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp],
+    "bsde_orthonormalize_shape": [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int],
     "bsde_basis_eval": [_vp, C.c_int, C.c_int, _i64, _vp, _vp, C.c_int, _vp],
 }
 

@@ -11,6 +11,15 @@ from scipy.special import legendre
 from bsde_solver._lib import BASIS_LEGENDRE, BASIS_POLY
 
 
+class BasisValues(xp.ndarray):
+    """The (N, p) array `basis.eval(x)` returns for a host x, remembering what it is: `basis_tag` = (kind, p, coef, x) with x
+    the contiguous host copy of the points.  ALS / SALSA given a list of such arrays (directly or wrapped in TensorCore)
+    ship x instead of the p basis rows and evaluate the basis inside the kernels (a quarter of the PCIe traffic at p = 4, and
+    the fused kernels).  The values are READ-ONLY so that the tag cannot go stale; arithmetic on them gives plain arrays
+    without a tag (the tag is not inherited by views or results)."""
+    basis_tag = None
+
+
 class Basis:
     kind = None
     degree = 0
@@ -23,9 +32,19 @@ class Basis:
 
         be = get_backend()
         on_device = hasattr(x, "is_cuda")
-        xd = x if on_device else be.to_device(xp.asarray(x, dtype=xp.float64).ravel())
+        xh = None if on_device else xp.array(x, dtype=xp.float64).ravel()       # always a private copy (it is made read-only below)
+        xd = x if on_device else be.to_device(xh)
         out = be.basis_eval(self.kind, self.degree, xd, self._coef(), deriv)      # [p][N]
-        return out.T if on_device else out.cpu().numpy().T
+        if on_device:
+            return out.T
+        rows = out.cpu().numpy()                  # (p, N) C-order; the reference returns its transpose, an F-ordered (N, p) view
+        if deriv != 0:
+            return rows.T
+        rows.flags.writeable = False
+        xh.flags.writeable = False
+        vals = rows.T.view(BasisValues)
+        vals.basis_tag = (self.kind, self.degree, self._coef(), xh)
+        return vals
 
     def eval(self, x):
         raise NotImplementedError("eval")

@@ -17,7 +17,7 @@ import numpy as np
 
 from bsde_solver import xp
 from bsde_solver._backend import BASIS_PHI, DeviceInputs, get_backend
-from bsde_solver._inputs import phis_list, stack_phis
+from bsde_solver._inputs import asset_blocks, phis_list, stack_phis, tagged_points  # noqa: F401
 from bsde_solver.core.optimisation.solve import solver, solver_id  # noqa: F401  (solver re-exported as in the reference)
 from bsde_solver.core.tensor.tensor_core import TensorCore  # noqa: F401
 from bsde_solver.core.tensor.tensor_network import TensorNetwork  # noqa: F401
@@ -53,12 +53,20 @@ def ALS(phis, result, n_iter=10, ranks=None, optimizer="lstsq", init_tt=None):
         y = result if _is_device_tensor(result) else be.to_device(np.asarray(result, dtype=np.float64).ravel())
         info = be.fit_als(phis, y, n_iter, tt_ranks, sid, flat)
     else:
-        host = stack_phis(phis)
         y = np.ascontiguousarray(np.asarray(result, dtype=np.float64).ravel())
-        if y.shape[0] != host.shape[2]:
-            raise ValueError(f"result has {y.shape[0]} samples, phis have {host.shape[2]}")
-        info = be.fit_als_host(BASIS_PHI, host.shape[0], host.shape[1], host.shape[2], host, None, y, n_iter, tt_ranks,
-                               sid, flat)
+        tagged = tagged_points(phis)
+        if tagged is not None:
+            # basis values of this package's own basis objects: ship the points, evaluate the basis in the kernels
+            kind, p, coef, blocks = tagged
+        else:
+            # arbitrary basis values: the (N, p) arrays' transposes are consumed where they lie (no stacked host copy)
+            kind, coef, blocks = BASIS_PHI, None, asset_blocks(phis)
+            p = blocks[0].shape[0]
+        if y.shape[0] != blocks[0].shape[-1]:
+            raise ValueError(f"result has {y.shape[0]} samples, phis have {blocks[0].shape[-1]}")
+        info = be.fit_als_host_assets(kind, p, blocks, coef, y, n_iter, tt_ranks, sid, flat)
+        last_fit_info["inputs"] = "points (tagged basis values)" if tagged is not None else "explicit basis values"
+
     last_fit_info.update(cholesky=int(info[0]), jacobi=int(info[1]), lu=int(info[2]), min_rank=int(info[3]))
     return unpack_cores(tt, tt_ranks, flat)
 

@@ -20,6 +20,9 @@ class TensorCore(xp.ndarray):
         obj.indices = tuple(indices) if indices is not None else cls._generate_indices(obj.shape_info)
         obj.base_shape = obj.shape
         obj.base_indices = obj.indices
+        # basis values produced by this package's own basis objects say so (core/calculus/basis.py: BasisValues); the tag is
+        # taken over by this wrapper only — not by views, slices or results of arithmetic (see __array_finalize__)
+        obj.basis_tag = getattr(input_array, "basis_tag", None) if obj.shape == getattr(input_array, "shape", None) else None
         return obj
 
     def __array_finalize__(self, obj):
@@ -27,6 +30,7 @@ class TensorCore(xp.ndarray):
             return
         for attr in ("shape_info", "indices", "name", "base_shape", "base_indices"):
             setattr(self, attr, getattr(obj, attr, None))
+        self.basis_tag = None
 
     def _describe(self):
         return ", ".join(f"{i} {{{s}}}" for i, s in zip(self.indices, self.shape_info))

@@ -56,11 +56,9 @@ class TensorTrain(TensorNetwork):
             raise ValueError("orthogonality must be either 'left' or 'right'")
         from bsde_solver._backend import get_backend
 
-        p = {c.shape[1] for c in self.cores.values()}
-        if len(p) != 1:
-            raise ValueError("the CUDA backend needs the same number of basis functions on every core")
+        shape = [int(c.shape[1]) for c in self.cores.values()]          # per-core basis sizes may differ (tensor_train.py:18-32)
         ranks, flat = pack_cores(self)
-        get_backend().orthonormalize(p.pop(), ranks, flat, 1 if mode == "right" else 0, start, stop)
+        get_backend().orthonormalize(shape[0] if len(set(shape)) == 1 else shape, ranks, flat, 1 if mode == "right" else 0, start, stop)
         unpack_cores(self, ranks, flat)
 
     @staticmethod

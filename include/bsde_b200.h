@@ -107,6 +107,13 @@ BSDE_API int bsde_fit_als_host(bsde_ctx* ctx, int basis_kind, int d, int p, int6
                       const double* coef_host, const double* y_host, int n_iter, const int* ranks, int solver_id,
                       double* cores_host, int* info_host);
 
+/* same, with one host block per asset: asset_ptrs_host[j] points at the N values x_j (POLY / LEGENDRE) or at asset j's p
+ * basis rows [p][N] (PHI) — the reference's `phis` list is d separate (N, p) F-ordered arrays (core/calculus/basis.py:21),
+ * whose transposes are exactly such blocks, so the list is consumed where it lies, without a stacked host copy */
+BSDE_API int bsde_fit_als_host_assets(bsde_ctx* ctx, int basis_kind, int d, int p, int64_t N, const double* const* asset_ptrs_host,
+                             const double* coef_host, const double* y_host, int n_iter, const int* ranks, int solver_id,
+                             double* cores_host, int* info_host);
+
 /* ---- SALSA   (replaces SALSA, core/optimisation/als.py:99-323) -------------------------------------------
  * ranks          : in = current bond ranks of cores_host; out = ranks after adaptation (d+1 ints)
  * init_ranks     : the ranks the TensorTrain object was constructed with (the reference's stale tt.ranks, als.py:122-123)
@@ -156,6 +163,19 @@ BSDE_API int bsde_solve(bsde_ctx* ctx, int n, const double* A_host, const double
                int* info_host);
 /* TensorTrain.orthonormalize (tensor_train.py:34-87) on the device; mode 0 = left, 1 = right */
 BSDE_API int bsde_orthonormalize(bsde_ctx* ctx, int d, int p, const int* ranks, double* cores_host, int mode, int start, int stop);
+/* the same for a train whose cores have their own basis sizes shape[j] (TensorTrain(shape, ranks) accepts a ragged
+ * shape, tensor_train.py:18-32); cores_host holds core j as (ranks[j], shape[j], ranks[j+1]) */
+BSDE_API int bsde_orthonormalize_shape(bsde_ctx* ctx, int d, const int* shape, const int* ranks, double* cores_host, int mode,
+                              int start, int stop);
+/* One SVD move of SALSA's sweep on a pair of host cores (teacher-forced parity of als.py:240-277 and of rank_adaptation,
+ * als.py:185-211).  side 0 = the move on the bond LEFT of core j: core_a = core_{j-1} (ra, p, k), core_b = core_j (k, p, rb);
+ * SVD of left_unfold(core_a) = U S Vt, core_a <- U, core_b <- (S * Vt) @ right_unfold(core_b), one more rank when
+ * `expand` (the host's expand_rank && k < max_ranks[j-1]) and S[-1] > min_sv.  side 1 = the move on the bond RIGHT of
+ * core j: core_a = core_j (ra, p, k), core_b = core_{j+1} (k, p, rb); core_a <- U S, core_b <- Vt @ right_unfold(core_b).
+ * Both buffers must have room for rank k + 1.  reg_out_host (>= k + 1 doubles, filled when do_reg): gamma resp. theta =
+ * nan_to_num(1 / max(S, min_sv)).  rank_out: the bond rank afterwards; adapted_out: 1 when it grew. */
+BSDE_API int bsde_salsa_move(bsde_ctx* ctx, int side, int ra, int p, int k, int rb, double min_sv, int expand, int do_reg,
+                    double* core_a_host, double* core_b_host, double* reg_out_host, int* rank_out, int* adapted_out);
 /* basis values / derivatives as the fused kernels compute them: out_dev [p][N] for one input vector x_dev [N] */
 BSDE_API int bsde_basis_eval(bsde_ctx* ctx, int basis_kind, int p, int64_t N, const double* x_dev, const double* coef_host,
                     int deriv, double* out_dev);

@@ -46,19 +46,26 @@ def _find_path(labels, shapes, out):
     ids = list(range(len(live)))
     path = []
     reverse = os.environ.get("BSDE_SHIM_ORDER", "greedy") == "reverse"
+    # (label -> number of live operands carrying it: a label survives a pairwise contraction when it is an output label
+    #  or some OTHER live operand carries it.  Same choices as the plain O(n^4) search, found ~100x faster, so that the
+    #  d = 100 trains of bench.py --impl reference do not spend minutes here.)
+    count = {}
+    for ls in live:
+        for l in set(ls):
+            count[l] = count.get(l, 0) + 1
+    outset = set(out)
     while len(live) > 1:
         best = None
         n = len(live)
+        sets = [set(ls) for ls in live]
         cand = [(i, j) for i in range(n) for j in range(i + 1, n)]
         if reverse:
             cand = cand[::-1]
         for i, j in cand:
-            shared = (set(live[i]) & set(live[j])) - {"batch"}
-            others = set(out)
-            for k in range(n):
-                if k != i and k != j:
-                    others |= set(live[k])
-            res = [l for l in dict.fromkeys(live[i] + live[j]) if l in others]
+            si, sj = sets[i], sets[j]
+            shared = (si & sj) - {"batch"}
+            res = [l for l in dict.fromkeys(live[i] + live[j])
+                   if l in outset or count[l] - (1 if l in si else 0) - (1 if l in sj else 0) > 0]
             size = 1
             for l in res:
                 size *= sizes[l]
@@ -67,6 +74,12 @@ def _find_path(labels, shapes, out):
                 best = (key, i, j, tuple(res))
         _, i, j, res = best
         path.append((i, j))
+        for l in sets[i]:
+            count[l] -= 1
+        for l in sets[j]:
+            count[l] -= 1
+        for l in set(res):
+            count[l] = count.get(l, 0) + 1
         live = [live[k] for k in range(n) if k != i and k != j] + [res]
     return path
 

@@ -61,12 +61,21 @@ def test_orthonormalize_matches_reference(backend, golden, case, mode, start, st
     g = golden("orthonormalize.npz")
     cores = cores_from(g, "in_")
     ranks = ranks_of(cores)
-    # ragged p per core in the fixture: the device kernel needs one p, so compare on a uniform-p train built the same way
-    if len({c.shape[1] for c in cores}) != 1:
-        pytest.skip("fixture has ragged basis sizes")
-    out = backend.orthonormalize(cores[0].shape[1], ranks, flat(cores), 1 if mode == "right" else 0, start, stop)
+    # the fixture's train has its own basis size on every core (shape (3, 4, 3, 3, 4)), as TensorTrain(shape, ranks) allows
+    shape = [c.shape[1] for c in cores]
+    assert len(set(shape)) > 1
+    out = backend.orthonormalize(shape, ranks, flat(cores), 1 if mode == "right" else 0, start, stop)
     ref = cores_from(g, case)
     assert rel(out, flat(ref)) < 1e-13
+    # and through the reference-shaped class
+    from bsde_solver.core.tensor.tensor_core import TensorCore
+    from bsde_solver.core.tensor.tensor_train import TensorTrain
+
+    tt = TensorTrain(shape, list(ranks))
+    for i, c in enumerate(cores):
+        tt.cores[f"core_{i}"] = TensorCore.like(c, tt.cores[f"core_{i}"])
+    tt.orthonormalize(mode=mode, start=start, stop=stop)
+    assert rel(flat([np.asarray(c) for c in tt.cores.values()]), flat(ref)) < 1e-13
 
 
 def test_orthonormalize_against_oracle(backend):

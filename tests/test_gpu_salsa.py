@@ -160,3 +160,78 @@ def test_salsa_step0_identical_samples(backend):
     print("step-0 fit", fit[:2], "oracle", ref_fit[:2], "mean(y)", y.mean(), "state", state[:3])
     assert np.isfinite(fit).all() and np.ptp(fit) < 1e-12
     assert abs(fit[0] - ref_fit[0]) < 1e-6 * abs(ref_fit[0])
+
+
+# ------------------------------------------------------------------------------- teacher-forced: one move at a time
+def _products(core_a, core_b):
+    """The two-core contraction: invariant under the sign / rotation gauge of the SVD."""
+    return core_a.reshape(-1, core_a.shape[2]) @ core_b.reshape(core_b.shape[0], -1)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_salsa_moves_teacher_forced(backend, golden, tag, monkeypatch):
+    """Every SVD move (als.py:240-277) and every rank decision (rank_adaptation, als.py:185-211, :249) of the run the CPU
+    suite pins to the reference fixture, replayed on the GPU ONE MOVE AT A TIME from the oracle's state: the chaos of the
+    end-to-end trajectory cannot build up, so decisions must be exact and numbers tight."""
+    g = golden(f"salsa_{tag}.npz")
+    x, y, p, r = g["x"], g["y"], int(g["p"]), int(g["r"])
+    d = x.shape[1]
+    ranks0 = [1] + [r] * (d - 1) + [1]
+    phis = [O.poly_eval(x[:, i], p) for i in range(d)]
+    moves = []
+    left, right = O.salsa_move_left_bond, O.salsa_move_right_bond
+
+    def rec_left(core_prev, core_curr, min_sv, expand, max_rank_bond, do_reg):
+        out = left(core_prev, core_curr, min_sv, expand, max_rank_bond, do_reg)
+        moves.append((0, core_prev.copy(), core_curr.copy(), min_sv, bool(expand) and core_prev.shape[2] < max_rank_bond, do_reg, out))
+        return out
+
+    def rec_right(core_curr, core_next, min_sv, do_reg):
+        out = right(core_curr, core_next, min_sv, do_reg)
+        moves.append((1, core_curr.copy(), core_next.copy(), min_sv, False, do_reg, out + (False,)))
+        return out
+
+    monkeypatch.setattr(O, "salsa_move_left_bond", rec_left)
+    monkeypatch.setattr(O, "salsa_move_right_bond", rec_right)
+    O.salsa(phis, y, n_iter=int(g["n_iter"]), ranks=ranks0, cores=cores_from(g, "init_"), max_rank=int(g["max_rank"]),
+            randomize=False, init_ranks=ranks0)
+    assert len(moves) == int(g["n_svds"])
+    grown = 0
+    for k, (side, ca, cb, min_sv, expand, do_reg, ref) in enumerate(moves):
+        # the oracle's input of move k IS the reference's (fixture svd_in_k; pinned on the CPU for the first sweeps)
+        assert ca.reshape(-1, ca.shape[2]).shape == g[f"svd_in_{k}"].shape, k
+        a, b, reg, adapted = backend.salsa_move(side, ca, cb, min_sv, expand=expand, do_reg=do_reg)
+        ra, rb, rreg, radapted = ref
+        assert adapted == radapted, (k, side)                      # rank decision: exact
+        assert a.shape == ra.shape and b.shape == rb.shape, k      # bond rank afterwards: exact
+        grown += int(adapted)
+        assert rel(_products(a, b), _products(ra, rb)) < 1e-12, (k, side)
+        if do_reg:
+            np.testing.assert_allclose(reg, rreg, rtol=1e-10, atol=0)
+        # orthonormal factor: U^T U = I (left move), and the moved factor carries the singular values (right move)
+        if side == 0:
+            u = a.reshape(-1, a.shape[2])
+            np.testing.assert_allclose(u.T @ u, np.eye(u.shape[1]), atol=1e-13)
+    assert grown > 0 or tag == "a"
+    print(f"salsa_{tag}: {len(moves)} moves replayed, {grown} rank adaptations")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_salsa_reference_svd_inputs_and_systems(backend, golden, tag):
+    """Straight from the reference fixture, no oracle in between: the singular values of every matrix the reference handed
+    to numpy.linalg.svd (svd_in_k -> svd_S_k), and the solution of every regularised system it solved (A_k, b_k -> x_k)."""
+    g = golden(f"salsa_{tag}.npz")
+    p = int(g["p"])
+    for k in range(int(g["n_svds"])):
+        M, S = g[f"svd_in_{k}"], g[f"svd_S_{k}"]
+        m, kk = M.shape
+        assert m % p == 0
+        _, _, inv_s, _ = backend.salsa_move(1, M.reshape(m // p, p, kk), np.zeros((kk, p, 1)), 1e-300, do_reg=True)
+        np.testing.assert_allclose(1.0 / inv_s, S, rtol=1e-11, atol=1e-14 * S[0])
+    worst = 0.0
+    for k in range(int(g["n_solves_kept"])):
+        A, b, xr = g[f"A_{k}"], g[f"b_{k}"], g[f"x_{k}"]
+        xs, info = backend.solve(A, b, 0)
+        worst = max(worst, np.linalg.norm(A @ (xs - xr)) / np.linalg.norm(b))
+        assert np.linalg.norm(A @ (xs - xr)) < 1e-9 * np.linalg.norm(b), k
+    print(f"salsa_{tag}: {int(g['n_svds'])} SVDs, {int(g['n_solves_kept'])} systems, worst |A (x - x_ref)| / |b| = {worst:.1e}")
