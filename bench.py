@@ -196,6 +196,160 @@ def workload_config(world):
             "l2": "inputs (839 MB/GPU) and interfaces (3.3 GB/GPU) exceed the 126 MB L2; no flush needed"}
 
 
+def load_full_solve():
+    """bench/full_solve.py as a module (bench.py itself shadows the name `bench`)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bsde_full_solve", os.path.join(ROOT, "bench", "full_solve.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+CONV_D = 20       # largest asset count at which the rank-4 / 4-monomial ALS fit of Black-Scholes data converges (d >= 50 does not,
+                  # neither here nor in the numpy restatement of the reference: DESIGN.md section 9)
+
+
+def converging_leg(be, torch, dist, rank, world, N, barrier):
+    """The C3 kernel shape (r = p = 4, n = 64) on a problem the train DOES fit: the terminal regression of the full solve
+    below — X_T of the Black-Scholes forward SDE (X0 = (1, 0.5, ...), sigma = 0.4, 50 Euler steps), y = g(X_T) = |x|^2.
+    Once the fit converges most normal equations are numerically rank-deficient and their solves truncate like
+    numpy.linalg.lstsq (vh_lstsq.cuh) instead of taking the LDL^T fast path."""
+    from bsde_solver._backend import BASIS_POLY, DeviceInputs
+
+    d = CONV_D
+    x0 = np.tile([1.0, 0.5], d // 2)
+    x, _ = be.paths_simulate(0, np.array([0.05, 0.4]), x0, N, 50, 1.0, seed=4242, sample_offset=rank * N, keep_xi=False)
+    xT = x[50].contiguous()
+    del x
+    y = be.terminal(0, np.array([0.05, 0.4]), xT)
+    inp = DeviceInputs(BASIS_POLY, P, xT)
+    rng = np.random.RandomState(11)
+    ranks = np.array([1] + [R] * (d - 1) + [1], dtype=np.int32)
+    init = np.concatenate([(rng.rand(ranks[i] * P * ranks[i + 1]) - 0.5) * 2 for i in range(d)])
+    info = None
+
+    def fit():
+        nonlocal info
+        cores = init.copy()
+        info = be.fit_als(inp, y, N_SWEEPS, ranks, 0, cores)
+        return cores
+
+    for _ in range(2):
+        fit()
+    barrier()
+    K = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        cores = fit()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    res = float(torch.linalg.vector_norm(be.tt_eval(inp, ranks, cores) - y) / torch.linalg.vector_norm(y))
+    micro = 2 * (d - 1) * N_SWEEPS
+    flops = N * N_SWEEPS * ((2 * (d - 2)) * algorithmic_flops_per_sample(R * P * R) + 2 * algorithmic_flops_per_sample(P * R))
+    return {"workload": f"Black-Scholes law d={d}, N=2^{int(np.log2(N))} per GPU, rank {R}, {P} monomials, y = |x|^2, {N_SWEEPS} sweeps/fit "
+                        f"({micro} micro-steps/fit)",
+            "value": world * N * N_SWEEPS * K / (ms * 1e-3), "unit": "samples*sweeps/s", "ms_per_fit": ms / K, "fits_timed": K,
+            "us_per_micro_step": 1e3 * ms / K / micro,
+            "fraction_of_fp64_peak_whole_fit": flops / (ms / K * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+            "fit_relative_residual": res,
+            "solves_per_fit": {"cholesky": int(info[0]), "truncated": int(info[1]), "lu": int(info[2]), "min_numerical_rank": int(info[3])}}
+
+
+def host_list_leg(be, torch, xT, y, ranks, init):
+    """The reference's calling convention at C3 size: ALS(phis, y) with host lists of (N, p) arrays, twice — the arrays this
+    package's own PolynomialBasis produces (recognised, shipped as points) and anonymous copies of them (explicit values)."""
+    from bsde_solver.core.calculus.basis import PolynomialBasis
+    from bsde_solver.core.optimisation import als as A
+    from bsde_solver.core.tensor.tensor_core import TensorCore
+    from bsde_solver.core.tensor.tensor_train import TensorTrain
+
+    xh, yh = xT.cpu().numpy(), y.cpu().numpy()
+    basis = PolynomialBasis(P)
+    tagged = [TensorCore(basis.eval(xh[i]), name=f"phi_{i+1}", indices=("batch", f"m_{i+1}")) for i in range(D)]
+    tt_ranks = tuple(int(r) for r in ranks)
+
+    def replay(self):                       # same initial cores as the other legs (the reference draws them from numpy's stream)
+        off = 0
+        for k, name in enumerate(self.cores):
+            n = self.cores[name].size
+            self.cores[name][:] = init[off:off + n].reshape(self.cores[name].shape)
+            off += n
+        return self
+
+    out = {}
+    orig = TensorTrain.randomize
+    TensorTrain.randomize = replay
+    try:
+        for label, phis in (("tagged", tagged), ("plain", None)):
+            if phis is None:
+                phis = [np.asfortranarray(np.array(t)) for t in tagged]          # anonymous F-ordered (N, p) copies, as the reference builds them
+                del tagged
+            A.ALS(phis, yh, n_iter=N_SWEEPS, ranks=tt_ranks)                      # warm-up (workspaces, plans)
+            torch.cuda.synchronize()
+            reps = 2
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                A.ALS(phis, yh, n_iter=N_SWEEPS, ranks=tt_ranks)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            h2d = sum(int(np.asarray(p_).nbytes) for p_ in phis) if label == "plain" else int(xh.nbytes)
+            out[label] = {"value": xh.shape[1] * N_SWEEPS / dt, "unit": "samples*sweeps/s", "ms_per_step": 1e3 * dt,
+                          "h2d_bytes_per_step": h2d + int(yh.nbytes), "inputs": A.last_fit_info.get("inputs"),
+                          "timing": "host wall clock around ALS(phis, y) incl. the H2D copies from pageable memory and the cores coming back"}
+    finally:
+        TensorTrain.randomize = orig
+    return out
+
+
+def multi_gpu_check(be, torch, dist, rank, world, local, N_check=1 << 18, sweeps=6):
+    """What tests/multigpu_check.py asserts, inside the driver-visible run: every rank ends a sharded fit with bit-identical
+    cores, and that fit equals the single-GPU fit of the union of the shards (fresh single-GPU context on rank 0).  Run on
+    the converging workload's law (Black-Scholes, d = CONV_D): on the C3 throughput data the fit explains nothing
+    (residual 0.9995) and its cores are not a function of the data to any useful accuracy."""
+    from bsde_solver._backend import BASIS_POLY, Backend, DeviceInputs
+
+    d = CONV_D
+    par = np.array([0.05, 0.4])
+    x0 = np.tile([1.0, 0.5], d // 2)
+    rng = np.random.RandomState(5)
+    ranks = np.array([1] + [R] * (d - 1) + [1], dtype=np.int32)
+    init = np.concatenate([(rng.rand(ranks[i] * P * ranks[i + 1]) - 0.5) * 2 for i in range(d)])
+
+    def data(b, lo, n):
+        x, _ = b.paths_simulate(0, par, x0, n, 10, 1.0, seed=909, sample_offset=lo, keep_xi=False)
+        xT = x[10].contiguous()
+        return xT, b.terminal(0, par, xT)
+
+    xs, ys = data(be, rank * N_check, N_check)
+    cores = init.copy()
+    be.fit_als(DeviceInputs(BASIS_POLY, P, xs), ys, sweeps, ranks, 0, cores)
+    t = torch.from_numpy(cores).cuda()
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    identical = bool(all(torch.equal(g, gathered[0]) for g in gathered))
+    err = res = None
+    if rank == 0:
+        single = Backend(device=local)                    # world = 1 inside the library: no exchange
+        xu, yu = data(single, 0, N_check * world)
+        full = init.copy()
+        single.fit_als(DeviceInputs(BASIS_POLY, P, xu), yu, sweeps, ranks, 0, full)
+        inp = DeviceInputs(BASIS_POLY, P, xu)
+        f_single = single.tt_eval(inp, ranks, full)
+        f_shard = single.tt_eval(inp, ranks, cores)
+        err = float(torch.linalg.vector_norm(f_shard - f_single) / torch.linalg.vector_norm(f_single))
+        res = float(torch.linalg.vector_norm(f_shard - yu) / torch.linalg.vector_norm(yu))
+    dist.barrier()
+    return {"replicas_identical": identical, "vs_single_gpu": err, "fit_relative_residual": res,
+            "what": f"{sweeps}-sweep fit (Black-Scholes law d={d}, rank {R}, {P} monomials) on 2^{int(np.log2(N_check))} samples per rank: cores "
+                    "all-gathered and compared bit for bit; fitted values of the sharded fit vs the single-GPU fit of the union of the shards (relative L2)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +359,8 @@ def main():
     ap.add_argument("--samples", type=int, default=N_PER_GPU, help="samples per GPU (default: the C3 workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the converging-fit, full-solve, host-list and multi-GPU-check legs")
+    ap.add_argument("--full-solve-assets", type=int, default=20)
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="library option for A/B measurements (bsde_ctx_set_option), e.g. fuse_interface=0")
     args = ap.parse_args()
@@ -251,7 +407,7 @@ def main():
     def fit_device():
         cores = init.copy()
         info = be.fit_als(inp, y, N_SWEEPS, ranks, 0, cores)
-        solve_paths.update(cholesky=int(info[0]), jacobi_svd=int(info[1]), lu=int(info[2]), min_numerical_rank=int(info[3]))
+        solve_paths.update(cholesky=int(info[0]), truncated=int(info[1]), lu=int(info[2]), min_numerical_rank=int(info[3]))
         return cores
 
     sampler = ClockSampler(local)
@@ -337,8 +493,27 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "assembly_traffic.json")) as f:
             roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        roofline["traffic_source"] = "static: ncu --set full capture of this kernel kept in profiles/assembly_traffic.json (not measured in this run)"
     except Exception:
         pass
+
+    # ---- what a fit that actually fits costs; a whole backward solve; the reference's calling convention; replica check ----
+    converging = full_solve = e2e_phis = mg_check = None
+    if not args.no_extras and N == N_PER_GPU:
+        converging = converging_leg(be, torch, dist, rank, world, N, barrier)
+        if world == 1 and not args.no_e2e:
+            e2e_phis = host_list_leg(be, torch, xT, y, ranks, init)
+        del xT, y, inp
+        torch.cuda.empty_cache()
+        if world > 1:
+            mg_check = multi_gpu_check(be, torch, dist, rank, world, local)
+        fs = load_full_solve().run(samples=1 << 20, assets=args.full_solve_assets, steps=50, rank=R, degree=P, sweeps=N_SWEEPS, seed=0,
+                                   model_name="bs")
+        if rank == 0:
+            full_solve = {k: fs[k] for k in ("workload", "n_gpus", "scaling", "paths_s", "solve_s", "total_s", "samples_sweeps_per_s", "Y0",
+                                             "Y0_reference", "Y0_reference_kind", "Y0_rel_err", "step_time_s_min_median_max")}
+            full_solve["note"] = ("largest explicit solve at rank 4 / 4 monomials that converges; BASELINE configs[2] itself (HJB d=100) diverges in the "
+                                  "reference algorithm too (DESIGN.md §9), as does Black-Scholes at d=100")
 
     # ---- CPU baseline on this host (rank 0, single-GPU runs only) ----
     cpu = None
@@ -355,6 +530,7 @@ def main():
             "config": workload_config(world) if N == N_PER_GPU else dict(workload_config(world), samples_per_gpu=N, workload="reduced-N debugging run (not the benchmark)"),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "fit_relative_residual": fit_quality, "solves_per_fit": solve_paths,
+            "converging": converging, "full_solve": full_solve, "e2e_phis": e2e_phis, "multi_gpu_check": mg_check,
             "allreduce": (None if world == 1 else ("fused into the reduction kernel over NVLink peer memory" if getattr(be, "p2p", False) else "ncclAllReduce")),
         }))
     if world > 1:

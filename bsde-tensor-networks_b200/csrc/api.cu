@@ -461,11 +461,36 @@ int als_sweep(bsde_ctx* c, const MicroCtx& m, int fused = 0, int first = 1) {
     return 0;
 }
 
-int px_check(bsde_ctx* c) {       // after a synchronised fit: did a peer wait time out?
+// Ranks are not synchronised when a fit starts (lazy module loads, plan allocation, a slow host): before the first fused
+// exchange of a fit every rank therefore joins a one-double ncclAllReduce on the fit's stream, so that no kernel starts
+// waiting for a peer that has not reached the fit yet.
+int px_handshake(bsde_ctx* c) {
+    if (!c->px_on || c->world <= 1) return 0;
+    BSDE_TRY(c->scalars.ensure(1024));
+    double* token = c->scalars.as<double>() + 120;
+    BSDE_CUDA_OK(cudaMemsetAsync(token, 0, sizeof(double), c->stream));
+    return allreduce_moments(c, token, 1);
+}
+
+// After a synchronised fit: did a wait for a peer time out on ANY rank?  (The rank that timed out continued on NaN sums; its
+// peers may have carried on with good ones: every rank must fail, or the replicas silently diverge.)
+int px_check(bsde_ctx* c) {
     if (!c->px_on) return 0;
     int err = 0;
     BSDE_CUDA_OK(cudaMemcpy(&err, c->px.error, sizeof err, cudaMemcpyDeviceToHost));
-    if (err) return fail_msg(3, "peer all-reduce timed out waiting for another rank (rank %d of %d)", c->rank, c->world);
+    double* token = c->scalars.as<double>() + 120;
+    const double mine = err ? 1.0 : 0.0;
+    BSDE_CUDA_OK(cudaMemcpyAsync(token, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    BSDE_TRY(allreduce_moments(c, token, 1));
+    double any = 0.0;
+    BSDE_CUDA_OK(cudaMemcpyAsync(&any, token, sizeof any, cudaMemcpyDeviceToHost, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (any != 0.0) {
+        const int zero = 0;
+        cudaMemcpy(c->px.error, &zero, sizeof zero, cudaMemcpyHostToDevice);
+        return fail_msg(3, "fused all-reduce: a wait for a peer timed out on %s (rank %d of %d); the fit's sums were poisoned with NaN",
+                        err ? "this rank" : "another rank", c->rank, c->world);
+    }
     return 0;
 }
 
@@ -495,6 +520,7 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
     BSDE_TRY(train_upload(c, T, d, p, ranks, nullptr, cores_host));
     int* info;
     BSDE_TRY(info_reset(c, &info));
+    BSDE_TRY(px_handshake(c));
     if (d >= 2) {
         // als.py:39 — tt.orthonormalize(mode="right", start=1)
         BSDE_TRY(launch_orthonormalize_right(T.cores, T.off_dev, T.ranks_dev, p, d, 1, d - 1, c->stream));
@@ -580,6 +606,7 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
     BSDE_TRY(train_upload(c, T, d, p, ranks, cap.data(), cores_host));
     int* info;
     BSDE_TRY(info_reset(c, &info));
+    BSDE_TRY(px_handshake(c));
     // device scalars: state = {eta, omega, min_sv}, residual sum, gamma[8], theta[8]; ints: adapted flag, new rank
     BSDE_TRY(c->scalars.ensure(1024));
     double* state = c->scalars.as<double>() + 32;
@@ -757,6 +784,11 @@ int bsde_ctx_launch_count(bsde_ctx* c, int64_t* out) {
 int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     BSDE_CHECK_CTX(c);
     if (name && !strcmp(name, "use_graph")) { c->use_graph = value; return 0; }
+    if (name && !strcmp(name, "px_timeout_ms")) {          // how long the fused all-reduce waits for a peer before it gives up
+        if (value < 1) return fail_msg(2, "px_timeout_ms must be positive");
+        c->px.timeout_cycles = (long long)value * 2000000ll;
+        return 0;
+    }
     if (name && !strcmp(name, "fuse_interface")) { c->fuse_interface = value; return 0; }
     if (name && !strcmp(name, "fast_solve")) { c->fast_solve = value; return 0; }
     if (name && !strcmp(name, "solve_stop")) { c->solve_stop = value; return 0; }
@@ -844,7 +876,7 @@ int bsde_comm_p2p_export(bsde_ctx* c, void* out128) {
         const size_t nf = (size_t)2 * kXMaxWorld * kXBlocks * sizeof(unsigned long long) + kXBlocks * sizeof(unsigned long long) + 64;
         BSDE_CUDA_OK(cudaMalloc(&c->px_data_local, nd));
         BSDE_CUDA_OK(cudaMalloc(&c->px_flags_local, nf));
-        BSDE_CUDA_OK(cudaMemset(c->px_data_local, 0, nd));
+        BSDE_CUDA_OK(cudaMemset(c->px_data_local, 0xFF, nd));        // every slot empty
         BSDE_CUDA_OK(cudaMemset(c->px_flags_local, 0, nf));
     }
     cudaIpcMemHandle_t h[2];

@@ -738,32 +738,43 @@ k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, in
 #pragma unroll
     for (int k = 0; k < kRedWarps; k++) t += part[k][lane];
     if (px.world > 1) {
-        // ---- fused all-reduce over NVLink peer memory: push this block's 32 sums into every rank's buffer, publish a
-        // flag per (source rank, block), wait for the same block of every other rank, add in rank order.  Every rank
-        // adds the same numbers in the same order, so all replicas end with bit-identical sums.  Buffers alternate
-        // with the parity of the launch count: a rank can only be one exchange ahead of the slowest one.
+        // ---- fused all-reduce over NVLink peer memory, ONE one-way trip on the critical path.  Every lane stores its sum
+        // straight into the slot (parity, source rank, slot) of every peer's buffer and then polls its own buffer until the
+        // peers' values have arrived: the data word is its own flag (8-byte stores are single-copy atomic; an empty slot
+        // holds a bit pattern no sum can take), so there is no fence, no flag store and no second round trip as in round 1
+        // (data, __threadfence_system, flag; then spin on the flags).  Consumed slots are emptied again by their reader; the
+        // writer can touch them next two exchanges later, which it starts only after it has seen this rank's NEXT exchange —
+        // issued by the next kernel of this stream, i.e. after the kernel boundary has made the emptying stores visible.
+        // Every rank adds the same numbers in rank order, so all replicas end with bit-identical sums.
+        const unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
         const int bid = blockIdx.y * gridDim.x + blockIdx.x;          // (row group, slot block): every group is exchanged on its own
-        const unsigned long long seq = px.step[bid] + 1;
+        const unsigned long long seq = px.step[bid];
         const size_t par = (size_t)(seq & 1ull) * px.world;
         const int slot = bid * 32 + lane;
-        for (int p = 0; p < px.world; p++) px.data[p][(par + px.rank) * kXSlots + slot] = t;
-        __threadfence_system();
-        __syncwarp();
-        if (lane < px.world)
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(px.flags[lane] + (par + px.rank) * kXBlocks + bid), "l"(seq) : "memory");
-        if (lane < px.world) {
-            const unsigned long long* f = px.flags[px.rank] + (par + lane) * kXBlocks + bid;
-            const long long t0 = clock64();
-            unsigned long long v;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-                if (v < seq && clock64() - t0 > 4000000000ll) { *px.error = 1; break; }     // ~2 s: a peer is gone
-            } while (v < seq);
-        }
-        __syncwarp();
+        for (int p = 0; p < px.world; p++)
+            if (p != px.rank)
+                asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(px.data[p] + (par + px.rank) * kXSlots + slot), "d"(t) : "memory");
+        double* mine = px.data[px.rank] + par * kXSlots + slot;
+        const double own = t;
         t = 0.0;
-        for (int q = 0; q < px.world; q++) t += __ldcg(px.data[px.rank] + (par + q) * kXSlots + slot);
-        if (lane == 0) px.step[bid] = seq;
+        bool late = false;
+        const long long t0 = clock64();
+        for (int q = 0; q < px.world; q++) {
+            double v = own;
+            if (q != px.rank) {
+                unsigned long long bits;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(mine + (size_t)q * kXSlots) : "memory");
+                    if (bits == kEmpty && clock64() - t0 > px.timeout_cycles) { late = true; break; }
+                } while (bits == kEmpty);
+                v = __longlong_as_double((long long)bits);
+                mine[(size_t)q * kXSlots] = __longlong_as_double((long long)kEmpty);
+            }
+            t += v;
+        }
+        if (late) { *px.error = 1; t = nan(""); }       // a peer is gone: the fit must not go on with partial sums
+        __syncwarp();
+        if (lane == 0) px.step[bid] = seq + 1;
     }
     if (e < n_slots) sums[e] = t;
 }

@@ -248,18 +248,32 @@ __device__ __forceinline__ bool has_diagonal_terms(const MicroSolveArgs& a) {
     return a.reg_diag != nullptr || a.ridge != 0.0 || a.eta_ptr != nullptr;
 }
 
+// 2^-k with 2^k <= m < 2^(k+1): multiplying the system by it is exact and brings its largest diagonal entry into [1, 2).
+// The normal equations of a long train can sit anywhere in the double range (interfaces are products of d factors: 1e-160
+// at d = 100 for Black-Scholes samples), and the acceptance tests and the Jacobi phase square their entries.
+__device__ __forceinline__ double pow2_normaliser(double m) {
+    if (!(m > 0.0) || !isfinite(m)) return 1.0;
+    int ex = (__double2hiint(m) >> 20) & 0x7ff;
+    if (ex == 0) return 0x1p+1000;                       // subnormal diagonal: lift it well into the normal range
+    ex = 2046 - ex;                                      // biased exponent of 2^-(ex - 1023)
+    if (ex > 2045) ex = 2045;
+    if (ex < 1) ex = 1;
+    return __hiloint2double(ex << 20, 0);
+}
+
 // Entry (i, j) of the system matrix as vh_lstsq reads it: an explicit matrix (bsde_solve), or the staged moments through
 // the expansion map with the regularised diagonal held in `diag` (n doubles; null = the plain moments).
 struct SystemMatrix {
     const double* direct;     // n x n row-major or null
     const double* stage;
     const uint16_t* map;
-    const double* diag;
+    const double* diag;       // already normalised
     int n;
+    double scale;             // power-of-two normalisation applied to direct / staged entries (pow2_normaliser)
     __device__ __forceinline__ double operator()(int i, int j) const {
-        if (direct) return direct[(size_t)i * n + j];
+        if (direct) return direct[(size_t)i * n + j] * scale;
         if (i == j && diag) return diag[i];
-        return stage[map[i * n + j]];
+        return stage[map[i * n + j]] * scale;
     }
 };
 
@@ -1095,13 +1109,23 @@ k_micro_solve_fast(MicroSolveArgs a) {
     for (int e = tid; e < a.n_slots; e += kFastThreads) stage[e] = load_moment(a, e);
     __syncthreads();
     // ---- equilibration, trace, positivity of the diagonal ----
-    if (tid < np) {
-        const double d = tid < n ? regularised_diagonal(a, tid, stage[dmap]) : 1.0;
-        sc[tid] = rsqrt(d);
-        dg[tid] = d;
-        if (tid < n) bv[tid] = stage[map[n * n + tid]];
+    if (tid < np) dg[tid] = tid < n ? regularised_diagonal(a, tid, stage[dmap]) : 0.0;
+    __syncthreads();
+    {   // normalise: largest diagonal entry into [1, 2) (exact; the solution does not change)
+        double mx = 0.0;
+        for (int i = tid & 31; i < n; i += 32) mx = fmax(mx, dg[i]);
+        mx = warp_max(mx);
+        const double nrm = pow2_normaliser(mx);
+        __syncthreads();
+        for (int e = tid; e < a.n_slots; e += kFastThreads) stage[e] *= nrm;
+        if (tid < np) {
+            const double d = tid < n ? dg[tid] * nrm : 1.0;
+            sc[tid] = rsqrt(d);
+            dg[tid] = d;
+        }
     }
     __syncthreads();
+    if (tid < n) bv[tid] = stage[map[n * n + tid]];
     if (tid < 32) {
         double tr = 0.0;
         int bad = 0;
@@ -1236,7 +1260,7 @@ k_micro_solve_fast(MicroSolveArgs a) {
         // ---- truncated minimum-norm solve (vh_lstsq.cuh); its scratch overlays the factorisation's buffers ----
         __syncthreads();
         __shared__ int s_sweeps;
-        const SystemMatrix Amat{nullptr, stage, map, has_diagonal_terms(a) ? dg : nullptr, n};
+        const SystemMatrix Amat{nullptr, stage, map, has_diagonal_terms(a) ? dg : nullptr, n, 1.0};      // stage is normalised already
         int rank = vh_lstsq<kFastThreads, 8, 4>(Amat, n, bv, xs, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
         if (rank < 0) {                       // moments that are not a Gram matrix (overflow, NaN): no answer
             for (int i = tid; i < n; i += kFastThreads) xs[i] = nan("");
@@ -1293,6 +1317,19 @@ k_micro_solve(MicroSolveArgs a) {
         for (int e = threadIdx.x; e < n; e += blockDim.x) a.dbg_A[n * n + e] = S.bvec[e];
     }
     __syncthreads();
+    // normalise the system (largest diagonal entry into [1, 2), exact): see pow2_normaliser
+    __shared__ double s_scale;
+    if (threadIdx.x < 32) {
+        double mx = 0.0;
+        for (int i = threadIdx.x; i < n; i += 32) mx = fmax(mx, S.A[i * ld + i]);
+        mx = warp_max(mx);
+        if (threadIdx.x == 0) s_scale = pow2_normaliser(mx);
+    }
+    __syncthreads();
+    const double nrm = s_scale;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) S.A[(e / n) * ld + (e % n)] *= nrm;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) S.bvec[e] *= nrm;
+    __syncthreads();
     if (a.solver == SOLVER_LSTSQ) {
         {
             const bool ok = cholesky_solve(S, n, S.x, s_red);
@@ -1329,9 +1366,9 @@ k_micro_solve(MicroSolveArgs a) {
                 // the regularised diagonal is parked in S.sc.
                 const bool diag = !a.A_direct && has_diagonal_terms(a);
                 if (diag)      // (S.A was scaled and factorised in place by the rejected Cholesky attempt)
-                    for (int i = threadIdx.x; i < n; i += blockDim.x) S.sc[i] = regularised_diagonal(a, i, stage_buf[a.expand_map[i * n + i]]);
+                    for (int i = threadIdx.x; i < n; i += blockDim.x) S.sc[i] = regularised_diagonal(a, i, stage_buf[a.expand_map[i * n + i]]) * nrm;
                 __syncthreads();
-                const SystemMatrix Amat{a.A_direct, stage_buf, a.expand_map, diag ? S.sc : nullptr, n};
+                const SystemMatrix Amat{a.A_direct, stage_buf, a.expand_map, diag ? S.sc : nullptr, n, nrm};
                 rank = vh_lstsq<kDenseThreads, 32, 3>(Amat, n, S.bvec, xtmp, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
                 if (rank >= 0 && a.clk && threadIdx.x == 0) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
             }
@@ -1344,6 +1381,9 @@ k_micro_solve(MicroSolveArgs a) {
                     __syncthreads();
                 } else {
                     expand_normal_equations(a, S.G, n, S.bvec, stage_buf);      // ld = n for the Jacobi kernels
+                    __syncthreads();
+                    for (int e = threadIdx.x; e < n * n; e += blockDim.x) S.G[e] *= nrm;
+                    for (int e = threadIdx.x; e < n; e += blockDim.x) S.bvec[e] *= nrm;
                     __syncthreads();
                     if (s_sym && !a.force_onesided) {
                         for (int e = threadIdx.x; e < n * n; e += blockDim.x) {      // exact symmetry: mirror the lower triangle

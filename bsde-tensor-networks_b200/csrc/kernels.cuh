@@ -49,10 +49,11 @@ constexpr int kXBlocks = 160;     // reduce-kernel blocks (32 slots each) that c
 constexpr int kXMaxWorld = 8;
 struct PeerExchange {
     int world = 1, rank = 0;
-    double* data[kXMaxWorld] = {};                 // data[p]  : rank p's buffer  [2][world][kXSlots]
-    unsigned long long* flags[kXMaxWorld] = {};    // flags[p] : rank p's flags   [2][world][kXBlocks]
-    unsigned long long* step = nullptr;            // local    : [kXBlocks] launches seen by each block
-    int* error = nullptr;                          // local    : set to 1 when a wait timed out
+    double* data[kXMaxWorld] = {};                 // data[p]  : rank p's buffer  [2][world][kXSlots], empty slots = all-ones bits
+    unsigned long long* flags[kXMaxWorld] = {};    // (round-1 protocol; the data words are their own flags now)
+    unsigned long long* step = nullptr;            // local    : [kXBlocks] exchanges done by each block (parity of the buffer)
+    int* error = nullptr;                          // local    : set to 1 when a wait timed out (the sums are then NaN)
+    long long timeout_cycles = 20000000000ll;      // ~10 s of SM clock; option "px_timeout_ms"
 };
 
 // Interface update fused into the assembly of the NEXT micro-step of an ALS half-sweep: the kernel forms the interface
