@@ -20,8 +20,8 @@ __global__ void __launch_bounds__(NT, 1) k_vh(const double* Ag, const double* bg
     double* base = xs + n; if ((size_t)(base - sm) & 1) base++;
     VhScratch S = vh_carve(base, n);
 #ifdef VH_PROFILE
-    __shared__ long long s_clk[8];
-    if (threadIdx.x < 8) s_clk[threadIdx.x] = 0;
+    __shared__ long long s_clk[16];
+    if (threadIdx.x < 16) s_clk[threadIdx.x] = 0;
     S.clk = s_clk;
 #endif
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) As[e] = Ag[e];
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(NT, 1) k_vh(const double* Ag, const double* bg
     for (int e = threadIdx.x; e < n; e += blockDim.x) x[e] = xs[e];
     if (threadIdx.x == 0) { info[0] = rank; info[1] = s_sweeps; clk[0] = t1 - t0;
 #ifdef VH_PROFILE
-        for (int k = 0; k < 8; k++) clk[1 + k] = s_clk[k];
+        for (int k = 0; k < 16; k++) clk[1 + k] = s_clk[k];
 #endif
     }
 }
@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
     int count = 0;
     if (fread(&count, 4, 1, f) != 1) return 1;
     double *dA, *db, *dx; int* dinfo; long long* dclk;
-    CK(cudaMalloc(&dA, 144 * 144 * 8)); CK(cudaMalloc(&db, 144 * 8)); CK(cudaMalloc(&dx, 144 * 8)); CK(cudaMalloc(&dinfo, 16)); CK(cudaMalloc(&dclk, 128));
+    CK(cudaMalloc(&dA, 144 * 144 * 8)); CK(cudaMalloc(&db, 144 * 8)); CK(cudaMalloc(&dx, 144 * 8)); CK(cudaMalloc(&dinfo, 16)); CK(cudaMalloc(&dclk, 256));
     CK(cudaFuncSetAttribute(k_vh<8, 4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_vh<32, 3, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_vh<16, 2, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -76,8 +76,8 @@ int main(int argc, char** argv) {
             for (int it = 0; it < 10; it++) launch();
             cudaEventRecord(e1); CK(cudaDeviceSynchronize());
             float ms; cudaEventElapsedTime(&ms, e0, e1);
-            int info[2]; long long clk; long long pc[9];
-            CK(cudaMemcpy(x.data(), dx, n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(info, dinfo, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(pc, dclk, 72, cudaMemcpyDeviceToHost)); clk = pc[0];
+            int info[2]; long long clk; long long pc[17];
+            CK(cudaMemcpy(x.data(), dx, n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(info, dinfo, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(pc, dclk, 136, cudaMemcpyDeviceToHost)); clk = pc[0];
             // error in the A-seminorm (fit space) relative to the reference's
             std::vector<double> dxv(n); for (int i = 0; i < n; i++) dxv[i] = x[i] - xref[i];
             double num = 0, den = 0, nx = 0, nr = 0;
@@ -85,7 +85,7 @@ int main(int argc, char** argv) {
             const double fiterr = sqrt(fabs(num) / fmax(den, 1e-300)), xerr = sqrt(nx / fmax(nr, 1e-300));
             printf(" rank %3d sweeps %2d %7.1f us (%lld cyc) fit-err %.1e x-err %.1e |", info[0], info[1], ms * 100.0, clk, fiterr, xerr);
 #ifdef VH_PROFILE
-            printf(" [chol %lld idx %lld load+dot %lld shfl %lld rot %lld apply %lld barrier %lld] ", pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
+            printf(" [chol %lld idx %lld load+dot %lld shfl %lld rot %lld apply %lld barrier %lld | chol: pre %lld argmax %lld rsqrt+dot %lld shfl %lld finish %lld barrier %lld] ", pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7], pc[9], pc[10], pc[11], pc[12], pc[13], pc[14]);
 #endif
             if (info[0] != rank_ref) mism[cfg]++;
             if (fiterr > worst[cfg]) worst[cfg] = fiterr;

@@ -647,6 +647,7 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
         }
         for (int j = 0; j < d; j++) {
             SalsaReg sr;
+            FusedInterface fi;
             sr.eta = state;
             if (j != 0) {
                 const int k = T.ranks[j];
@@ -664,10 +665,15 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
                     if (h[0]) { has_adapted = true; T.ranks[j] = h[1]; }
                 }
                 if (do_reg) { sr.gamma = gamma; sr.reg_left = 1; }
-                // L_j from the final core_{j-1}
-                BSDE_TRY(launch_interface_left(in, j - 1, T.core(j - 1), T.ranks[j - 1], T.ranks[j], j - 1 == 0 ? nullptr : B.at(j - 1),
-                                               B.at(j), c->stream));
-                c->launches++;
+                // L_j from the final core_{j-1}: formed inside this micro-step's assembly kernel (FusedInterface) where the
+                // shape allows it, by its own kernel otherwise (micro_step decides)
+                fi.side = 1; fi.j = j - 1; fi.r_in = T.ranks[j - 1]; fi.core = T.core(j - 1);
+                fi.in = j - 1 == 0 ? nullptr : B.at(j - 1); fi.out = B.at(j);
+                if (!(c->fuse_interface && basis_kind != BASIS_PHI)) {
+                    BSDE_TRY(launch_interface_left(in, j - 1, T.core(j - 1), T.ranks[j - 1], T.ranks[j], fi.in, fi.out, c->stream));
+                    c->launches++;
+                    fi.side = 0;
+                }
             }
             if (j != d - 1) {
                 BSDE_TRY(launch_salsa_right(T.core(j), T.core(j + 1), T.ranks[j], p, T.ranks[j + 1], T.ranks[j + 2], state + 2, do_reg,
@@ -689,7 +695,7 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
                 BSDE_TRY(launch_salsa_scalars(state, res_sum, n_total, freq_omega, 0, c->stream));
                 c->launches++;
             }
-            BSDE_TRY(micro_step(c, m, j, 0, 0.0, nullptr, nullptr, &sr));
+            BSDE_TRY(micro_step(c, m, j, 0, 0.0, nullptr, nullptr, &sr, fi.side ? &fi : nullptr));
         }
         // als.py:288-298 — residual of the last micro-step's design matrix with the new last core
         {

@@ -42,12 +42,13 @@ struct VhScratch {
     double* red;     // 8
     int* flags;      // 8
     unsigned short* tab;   // (m - 1) * m / 2 round-robin pairs, m = n rounded up to even
+    long long* keys;       // [2][32] per-warp pivot candidates of the Cholesky phase (double-buffered by step parity)
 };
 
 __host__ __device__ inline int vh_ldg(int n) { return ((n + 1) & ~1) + 8; }
 __host__ __device__ inline size_t vh_scratch_doubles(int n) {
     const size_t m = (size_t)((n + 1) & ~1);
-    return (size_t)n * vh_ldg(n) + 3 * (size_t)n + 8 + 8 + ((m - 1) * (m / 2) + 3) / 4 + 1;
+    return (size_t)n * vh_ldg(n) + 3 * (size_t)n + 8 + 8 + 64 + ((m - 1) * (m / 2) + 3) / 4 + 1;
 }
 
 __device__ __forceinline__ VhScratch vh_carve(double* base, int n) {
@@ -60,7 +61,8 @@ __device__ __forceinline__ VhScratch vh_carve(double* base, int n) {
     S.coef = S.lam + n;
     S.red = S.coef + n;
     S.flags = reinterpret_cast<int*>(S.red + 8);
-    S.tab = reinterpret_cast<unsigned short*>(S.red + 16);
+    S.keys = reinterpret_cast<long long*>(S.red + 16);
+    S.tab = reinterpret_cast<unsigned short*>(S.red + 16 + 64);
     return S;
 }
 
@@ -122,51 +124,82 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
     constexpr int TPR = T / 64 > 32 ? 32 : T / 64;
     constexpr int RPW = 32 / TPR;
     const int rowlocal = lane % RPW, sub = lane / RPW;
-    int r = 0;
-    for (int k = 0; k < n; k++) {
-        // every warp finds the pivot itself (no barrier between the search and the update).  One 64-bit key per row:
-        // the diagonal entry with the row index in its 8 lowest mantissa bits (pivot ties within 2^-44 go to the key
-        // order; the pivot VALUE is read back exactly) — one shuffle and one compare per butterfly stage.
+    // One 64-bit key per row for the pivot search: the diagonal entry with the row index in its 8 lowest mantissa bits
+    // (pivot ties within 2^-44 go to the key order; the pivot VALUE is read back exactly).  The keys of the rows a warp has
+    // just updated are reduced by that warp BEFORE the step's barrier (s_key[warp]); after it every warp only combines the
+    // nwarps keys, so the dependent chain between two steps is: barrier, one shared-memory load, log2(nwarps) shuffles.
+    constexpr int KIT = (2 * LP * UMAX + TPR - 1) / TPR;       // column-update iterations per lane (rows capacity / TPR)
+    static_assert(nwarps <= 32, "one key per warp");
+    auto make_key = [](double v, int i) -> long long {
+        return v > 0.0 ? ((__double_as_longlong(v) & ~0xffll) | (long long)(255 - i)) : LLONG_MIN;
+    };
+    {   // keys of the initial diagonal
         long long key = LLONG_MIN;
-        for (int i = lane; i < n; i += 32) {
-            const double v = d[i];
-            if (v > 0.0) { const long long kv = (__double_as_longlong(v) & ~0xffll) | (long long)(255 - i); key = kv > key ? kv : key; }
+        for (int i0 = warp * RPW; i0 < n; i0 += nwarps * RPW) {
+            const int i = i0 + rowlocal;
+            if (sub == 0 && i < n) { const long long kv = make_key(d[i], i); key = kv > key ? kv : key; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(full, key, o); key = ok > key ? ok : key; }
+        if (lane == 0) S.keys[warp] = key;
+    }
+    __syncthreads();
+    int r = 0;
+    for (int k = 0; k < n; k++) {
+        VH_T(8);
+        long long key = lane < nwarps ? S.keys[(k & 1) * 32 + lane] : LLONG_MIN;
+#pragma unroll
+        for (int o = (nwarps > 16 ? 16 : (nwarps > 8 ? 8 : (nwarps > 4 ? 4 : (nwarps > 2 ? 2 : 1)))); o > 0; o >>= 1) {
+            const long long ok = __shfl_xor_sync(full, key, o);
+            key = ok > key ? ok : key;
+        }
+        key = __shfl_sync(full, key, 0);
         if (key == LLONG_MIN) break;                   // nothing positive left (uniform over the CTA)
         const int jk = 255 - (int)(key & 0xff);
         const double bv = d[jk];
         if (!(bv > tolpiv)) break;
+        VH_T(9);
         const double inv = vh_rsqrt(bv), lkk = bv * inv;
         double* colk = G + (size_t)k * ldg;
+        long long mykey = LLONG_MIN;
         for (int i0 = warp * RPW; i0 < n; i0 += nwarps * RPW) {
             const int i = i0 + rowlocal;
             const bool live = i < n && i != jk && d[i] > -DBL_MAX;          // not selected yet
-            double part = 0.0, part1 = 0.0;
-            if (live) {
-                int t = sub;
-                for (; t + TPR < k; t += 2 * TPR) {
-                    part = fma(G[(size_t)t * ldg + i], G[(size_t)t * ldg + jk], part);
-                    part1 = fma(G[(size_t)(t + TPR) * ldg + i], G[(size_t)(t + TPR) * ldg + jk], part1);
-                }
-                if (t < k) part = fma(G[(size_t)t * ldg + i], G[(size_t)t * ldg + jk], part);
-                part += part1;
+            // row i of the factor times row jk, columns t = sub, sub + TPR, ... < k: all loads issued up front, four chains
+            double pa[4] = {0.0, 0.0, 0.0, 0.0};
+            const double* gi = G + (live ? i : jk) + (size_t)sub * ldg;
+            const double* gj = G + jk + (size_t)sub * ldg;
+#pragma unroll
+            for (int u = 0; u < KIT; u++) {
+                const int t = sub + u * TPR;
+                if (t < k) pa[u & 3] = fma(gi[(size_t)u * TPR * ldg], gj[(size_t)u * TPR * ldg], pa[u & 3]);
             }
+            double part = (pa[0] + pa[1]) + (pa[2] + pa[3]);
+            VH_T(10);
 #pragma unroll
             for (int o = RPW; o < 32; o <<= 1) part += __shfl_xor_sync(full, part, o);
+            VH_T(11);
             if (sub == 0 && i < n) {
                 if (live) {
                     const double v = (Aat(i, jk) - part) * inv;
                     colk[i] = v;
-                    d[i] = fma(-v, v, d[i]);
+                    const double dn = fma(-v, v, d[i]);
+                    d[i] = dn;
+                    const long long kv = make_key(dn, i);
+                    mykey = kv > mykey ? kv : mykey;
                 } else if (i == jk) {
                     colk[i] = lkk;
                     d[i] = -DBL_MAX;                   // selected: never a pivot again, no entries in later columns
                 }
             }
         }
+        // this warp's best remaining pivot (lanes with sub == 0 hold the rows' keys)
+#pragma unroll
+        for (int o = RPW >> 1; o > 0; o >>= 1) { const long long ok = __shfl_xor_sync(full, mykey, o); mykey = ok > mykey ? ok : mykey; }
+        if (lane == 0) S.keys[((k + 1) & 1) * 32 + warp] = mykey;
+        VH_T(12);
         __syncthreads();
+        VH_T(13);
         r = k + 1;
     }
     // positive semi-definite to working accuracy?  (Gram matrices always are; an explicit system may not be)
