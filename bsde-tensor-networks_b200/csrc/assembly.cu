@@ -287,7 +287,7 @@ __device__ __forceinline__ double stage_functions(const AsmArgs& a, double* __re
 }
 
 // ---- epilogue: fixed-order sum of the warps' tiles, one partial row per CTA ----
-template <int NT>
+template <int NT, int WARPS = kAsmWarps>
 __device__ __forceinline__ void write_partials(const AsmArgs& a, double* sm, double* ws, const double (&acc)[NT][2],
                                                double accyy, int lane, int tile_base, bool write_yy) {
 #pragma unroll
@@ -302,16 +302,16 @@ __device__ __forceinline__ void write_partials(const AsmArgs& a, double* sm, dou
     if (lane == 0) ws[NT * 64] = accyy;
     __syncthreads();
     double* out = a.partial + (int64_t)blockIdx.x * a.partial_stride;
-    for (int e = threadIdx.x; e < NT * 64; e += kAsmThreads) {
+    for (int e = threadIdx.x; e < NT * 64; e += WARPS * 32) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < kAsmWarps; w++) t += sm[(size_t)w * a.warp_doubles + e];
+        for (int w = 0; w < WARPS; w++) t += sm[(size_t)w * a.warp_doubles + e];
         out[(int64_t)tile_base * 64 + e] = t;
     }
     if (threadIdx.x == 0 && write_yy) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < kAsmWarps; w++) t += sm[(size_t)w * a.warp_doubles + NT * 64];
+        for (int w = 0; w < WARPS; w++) t += sm[(size_t)w * a.warp_doubles + NT * 64];
         out[a.partial_stride - 1] = t;
     }
 }
@@ -435,9 +435,16 @@ constexpr int kR4FmRows = 32;            // function-major rows: RR_0..7 | B_0..
 constexpr int kR4SmStride = 10;          // sample-major doubles per sample: RR_8, RR_9, L_0..3, 4 pad (conflict-free 16-byte reads)
 constexpr int kR4WarpDoubles = kR4FmRows * kStride + 32 * kR4SmStride;
 
-#ifndef BSDE_R4_MIN_BLOCKS
-#define BSDE_R4_MIN_BLOCKS 3
+// Warps per CTA (12 / kR4Warps CTAs per SM, 3 warps per scheduler either way).  Measured in round 2, same box, A/B: one CTA
+// of 12 warps per SM — a third of the partial rows for k_moment_reduce (148 instead of 444) — is SLOWER: assembly 96.2 vs
+// 93.0 us per launch (12-way epilogue sum, one barrier domain), reduce 8.35 vs 8.44 us (it is latency-, not data-bound):
+// 257.7 vs 251.8 ms per C3 fit.  Three CTAs of 4 warps stay.
+#ifndef BSDE_R4_WARPS
+#define BSDE_R4_WARPS 4
 #endif
+constexpr int kR4Warps = BSDE_R4_WARPS;
+constexpr int kR4Threads = kR4Warps * 32;
+constexpr int kR4MinBlocks = 12 / kR4Warps;
 // FULL = the interior launches of a C3..C5 sweep (192 of 196 per sweep at d = 100): fused interface update from a rank-4
 // neighbour, both bonds present with 4 components, N a multiple of 32.  Everything load_raw / fuse_interface decide at run
 // time for the general case (component counts, null bonds, tail masking, clamped sample index: ~150 integer / predicate
@@ -505,7 +512,7 @@ __device__ __forceinline__ void r4_fuse(const AsmArgs& a, const double* __restri
 }
 
 template <bool FULL>
-__global__ void __launch_bounds__(kAsmThreads, BSDE_R4_MIN_BLOCKS)
+__global__ void __launch_bounds__(kR4Threads, kR4MinBlocks)
 k_assemble_r4(AsmArgs a) {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -514,7 +521,7 @@ k_assemble_r4(AsmArgs a) {
     const double* score = sm + a.core_off;
     if (a.fuse) {
         const int nc = (a.fuse == 1 ? a.fr_in * a.rl : a.rr * a.fr_in) * a.in.p;
-        for (int e = threadIdx.x; e < nc; e += kAsmThreads) sm[a.core_off + e] = a.fcore[e];
+        for (int e = threadIdx.x; e < nc; e += kR4Threads) sm[a.core_off + e] = a.fcore[e];
     }
     ws[15 * kStride + lane] = 0.0;       // the ZERO function (samples 0..31 are all that is ever read)
     __syncthreads();
@@ -533,17 +540,17 @@ k_assemble_r4(AsmArgs a) {
     double accyy = 0.0;
 
     const int64_t nchunks = (a.in.N + 31) / 32;
-    const int64_t warps_total = (int64_t)gridDim.x * kAsmWarps;
+    const int64_t warps_total = (int64_t)gridDim.x * kR4Warps;
     RawSample<4, 4> raw;
 #ifndef BSDE_R4_NOPREFETCH
-    r4_load_raw<FULL>(a, lane, (int64_t)blockIdx.x * kAsmWarps + warp, nchunks, raw);
+    r4_load_raw<FULL>(a, lane, (int64_t)blockIdx.x * kR4Warps + warp, nchunks, raw);
 #endif
-    for (int64_t chunk = (int64_t)blockIdx.x * kAsmWarps + warp; chunk < nchunks; chunk += warps_total) {
+    for (int64_t chunk = (int64_t)blockIdx.x * kR4Warps + warp; chunk < nchunks; chunk += warps_total) {
 #ifdef BSDE_R4_NOPREFETCH
         r4_load_raw<FULL>(a, lane, chunk, nchunks, raw);      // 4 CTAs per SM: the other warps cover the DRAM latency
 #endif
 #ifdef BSDE_R4_EXPERIMENT_PHASE2_ONLY      // measurement only (wrong results): stage the first chunk, then DMMA phases alone
-        if (chunk == (int64_t)blockIdx.x * kAsmWarps + warp)
+        if (chunk == (int64_t)blockIdx.x * kR4Warps + warp)
 #endif
         {
         r4_fuse<FULL>(a, score, chunk * 32 + lane, raw);
@@ -617,7 +624,7 @@ k_assemble_r4(AsmArgs a) {
         }
         __syncwarp();
     }
-    write_partials<kR4Tiles>(a, sm, ws, acc, accyy, lane, 0, true);
+    write_partials<kR4Tiles, kR4Warps>(a, sm, ws, acc, accyy, lane, 0, true);
 }
 
 // =====================================================================================================
@@ -786,11 +793,11 @@ template <class K>
 int run_kernel(K kernel, int op, const AsmPlan& plan, const AsmArgs* args, cudaStream_t st, int* occ) {
     if (op == OP_OCCUPANCY) {
         BSDE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kernel, kAsmThreads, plan.smem_bytes));
+        BSDE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kernel, plan.warps * 32, plan.smem_bytes));
         return 0;
     }
     dim3 grid(plan.grid_x, plan.n_groups);
-    kernel<<<grid, kAsmThreads, plan.smem_bytes, st>>>(*args);
+    kernel<<<grid, plan.warps * 32, plan.smem_bytes, st>>>(*args);
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1001,11 +1008,12 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
     const int tiles_per_cta = P.rb_class >= 0 ? n_tiles : P.NJ;
     P.warp_doubles = std::max(P.F * kStride + 16, tiles_per_cta * 64 + 1);    // +16: look-ahead reads of the pipelined loop
     if (use_r4) P.warp_doubles = std::max(kR4WarpDoubles, kR4Tiles * 64 + 2);
-    P.core_off = (int)((size_t)kAsmWarps * P.warp_doubles + (((tab_smem + 15) & ~(size_t)15) / sizeof(double)));
+    P.warps = use_r4 ? kR4Warps : kAsmWarps;
+    P.core_off = (int)((size_t)P.warps * P.warp_doubles + (((tab_smem + 15) & ~(size_t)15) / sizeof(double)));
     P.smem_bytes = ((size_t)P.core_off + (size_t)8 * kMaxP * 8) * sizeof(double);      // + the neighbouring core of a fused interface update
     if (P.smem_bytes > 200 * 1024) return fail_msg(2, "assembly: core shape (%d,%d,%d) needs %zu B of shared memory", rl, p, rr, P.smem_bytes);
     const int64_t nchunks = (N + 31) / 32;
-    const int64_t want = (nchunks + kAsmWarps - 1) / kAsmWarps;
+    const int64_t want = (nchunks + P.warps - 1) / P.warps;
     int per_sm = 1;
     { const int rc = dispatch(OP_OCCUPANCY, P, nullptr, nullptr, &per_sm); if (rc) return rc; }
     if (per_sm < 1) per_sm = 1;

@@ -33,6 +33,7 @@ struct AsmPlan {
     int grid_x = 0;                               // CTAs along the sample axis (= number of partial rows)
     int64_t partial_stride = 0;                   // doubles per partial row = tiles*64 + 1
     int warp_doubles = 0;                         // shared-memory doubles per warp
+    int warps = 4;                                // warps per CTA of the kernel this plan launches
     int tab_entries = 0;
     int core_off = 0;                             // shared-memory offset (doubles) of the fused update's neighbouring core
     size_t smem_bytes = 0;
