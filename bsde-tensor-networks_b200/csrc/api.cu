@@ -1081,6 +1081,42 @@ int bsde_tt_grad(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const dou
     return 0;
 }
 
+int bsde_tt_hessian(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* dphi_dev,
+                    const double* d2phi_dev, const double* coef_host, const int* ranks, const double* cores_host, double* h_out_dev) {
+    BSDE_CHECK_CTX(c);
+    Guard g(c);
+    BSDE_TRY(check_ranks(d, p, ranks));
+    if (!cores_host || !h_out_dev) return fail_msg(2, "tt_hessian: null pointer");
+    if (basis_kind == BSDE_BASIS_PHI && (!dphi_dev || !d2phi_dev)) return fail_msg(2, "tt_hessian: explicit basis values need dphi_dev and d2phi_dev");
+    Inputs in;
+    BSDE_TRY(make_inputs(c, in, basis_kind, d, p, N, inputs_dev, dphi_dev, coef_host));
+    in.d2data = d2phi_dev;
+    Train T;
+    BSDE_TRY(train_upload(c, T, d, p, ranks, nullptr, cores_host));
+    if (T.max_rank() > 8) return fail_msg(2, "tt_hessian: ranks <= 8 supported");
+    Bonds B;
+    BSDE_TRY(bonds_alloc(c, T, N, B));
+    BSDE_TRY(build_right(c, T, in, B, 1));           // bond[k] = R_{k-1}
+    const int rmax = T.max_rank();
+    BSDE_TRY(c->tmp.ensure(sizeof(double) * 2 * (size_t)rmax * N + sizeof(double*) * (size_t)d + 64));
+    double* Lbuf[2] = {c->tmp.as<double>(), c->tmp.as<double>() + (size_t)rmax * N};
+    const double** rb_dev = (const double**)(c->tmp.as<double>() + 2 * (size_t)rmax * N);
+    std::vector<const double*> rb((size_t)d);
+    for (int j = 0; j < d; j++) rb[j] = j == d - 1 ? nullptr : B.at(j + 1);
+    BSDE_CUDA_OK(cudaMemcpyAsync(rb_dev, rb.data(), sizeof(double*) * (size_t)d, cudaMemcpyHostToDevice, c->stream));
+    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < d; i++) {
+        const double* Lin = i == 0 ? nullptr : Lbuf[i & 1];
+        BSDE_TRY(launch_hessian_row(in, i, T.cores, T.off_dev, T.ranks_dev, rb_dev, Lin, rmax, h_out_dev, c->stream));
+        c->launches++;
+        if (i < d - 1) {      // L_{i+1} = L_i . (C_i . phi_i)
+            BSDE_TRY(launch_interface_left(in, i, T.core(i), T.ranks[i], T.ranks[i + 1], Lin, Lbuf[(i + 1) & 1], c->stream));
+            c->launches++;
+        }
+    }
+    return 0;
+}
+
 static int model_params(int model_id, const double* params, double& r, double& sigma0) {
     if (!params) return fail_msg(2, "model params is null");
     if (model_id == BSDE_MODEL_BLACKSCHOLES) { r = params[0]; sigma0 = params[1]; return 0; }

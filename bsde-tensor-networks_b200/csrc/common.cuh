@@ -26,6 +26,7 @@ struct Inputs {
     int64_t N;              // samples on this GPU (also the leading stride)
     const double* data;     // X [d][N] or PHI [d][p][N]
     const double* ddata;    // dPHI [d][p][N] for BASIS_PHI gradients, else null
+    const double* d2data = nullptr;   // d2PHI [d][p][N] for BASIS_PHI Hessians, else null
     const double* coef;     // BASIS_LEGENDRE: [3][p][p] descending-power polyval coefficients (deriv order, i, k)
 };
 
@@ -94,7 +95,7 @@ __device__ __forceinline__ void basis_from_x(const Inputs& in, double x, int der
 template <int PB>
 __device__ __forceinline__ void basis_values(const Inputs& in, int j, int64_t s, int deriv, double (&phi)[PB]) {
     if (in.kind == BASIS_PHI) {
-        const double* src = (deriv == 0 ? in.data : in.ddata) + ((int64_t)j * in.p) * in.N + s;
+        const double* src = (deriv == 0 ? in.data : (deriv == 1 ? in.ddata : in.d2data)) + ((int64_t)j * in.p) * in.N + s;
 #pragma unroll
         for (int m = 0; m < PB; m++) phi[m] = (m < in.p) ? __ldg(src + (int64_t)m * in.N) : 0.0;
         return;

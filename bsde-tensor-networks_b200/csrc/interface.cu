@@ -10,6 +10,7 @@
 // stores, the core broadcast from shared memory, basis values evaluated in registers (never stored).
 #include "common.cuh"
 #include "kernels.cuh"
+#include <algorithm>
 
 namespace bsde {
 
@@ -245,6 +246,87 @@ k_grad_step(Inputs in, int i, const double* __restrict__ core, int rl, int rr,
     }
 }
 
+// Row i of the Hessian of the train at every sample (reference: core/calculus/hessian.py:6-26, O(d^2) contractions there):
+//   H_ii = L_i (C_i . ddphi_i) R_i,      H_ij = L_i (C_i . dphi_i) [prod_{i<k<j} (C_k . phi_k)] (C_j . dphi_j) R_j   (j > i)
+// one thread per sample carries the row vector v = L_i (C_i . dphi_i) prod (C_k . phi_k) to the right.  rbond[j] = R_j
+// (r_{j+1} slabs of N, null for the last core); out is H [d][d][N], both triangles written.
+struct HessArgs {
+    const double* cores;
+    const int64_t* core_off;      // device
+    const int* ranks;             // device
+    const double* const* rbond;   // device array of d pointers
+    const double* Lin;            // L_i (ranks[i] slabs) or null for i = 0
+    double* out;
+    int i;
+};
+
+template <int RB, int PB>
+__global__ void __launch_bounds__(kThreads)
+k_hessian_row(Inputs in, HessArgs h) {
+    const int64_t N = in.N;
+    const int d = in.d, p = in.p, i = h.i;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+        double v[RB], phi[PB], dphi[PB], ddphi[PB];
+        const int rl = h.ranks[i], rr = h.ranks[i + 1];
+        const double* C = h.cores + h.core_off[i];
+        basis_values<PB>(in, i, s, 1, dphi);
+        basis_values<PB>(in, i, s, 2, ddphi);
+#pragma unroll
+        for (int b = 0; b < RB; b++) v[b] = 0.0;
+        double w2[RB];                               // L_i (C_i . ddphi_i)
+#pragma unroll
+        for (int b = 0; b < RB; b++) w2[b] = 0.0;
+        for (int a = 0; a < rl; a++) {
+            const double la = h.Lin ? h.Lin[(int64_t)a * N + s] : 1.0;
+#pragma unroll
+            for (int m = 0; m < PB; m++)
+                if (m < p) {
+                    const double* c = C + (a * p + m) * rr;
+#pragma unroll
+                    for (int b = 0; b < RB; b++)
+                        if (b < rr) { v[b] = fma(la * dphi[m], c[b], v[b]); w2[b] = fma(la * ddphi[m], c[b], w2[b]); }
+                }
+        }
+        {
+            const double* R = h.rbond[i];
+            double hii = 0.0;
+#pragma unroll
+            for (int b = 0; b < RB; b++)
+                if (b < rr) hii = fma(w2[b], R ? R[(int64_t)b * N + s] : 1.0, hii);
+            h.out[((int64_t)i * d + i) * N + s] = hii;
+        }
+        for (int j = i + 1; j < d; j++) {
+            const int ra = h.ranks[j], rb = h.ranks[j + 1];
+            const double* Cj = h.cores + h.core_off[j];
+            const double* R = h.rbond[j];
+            basis_values<PB>(in, j, s, 0, phi);
+            basis_values<PB>(in, j, s, 1, dphi);
+            double nv[RB], hv = 0.0;
+#pragma unroll
+            for (int b = 0; b < RB; b++) nv[b] = 0.0;
+#pragma unroll
+            for (int a = 0; a < RB; a++) {
+                if (a < ra) {
+#pragma unroll
+                    for (int m = 0; m < PB; m++)
+                        if (m < p) {
+                            const double* c = Cj + (a * p + m) * rb;
+                            double u = 0.0;
+#pragma unroll
+                            for (int b = 0; b < RB; b++)
+                                if (b < rb) { nv[b] = fma(v[a] * phi[m], c[b], nv[b]); u = fma(c[b], R ? R[(int64_t)b * N + s] : 1.0, u); }
+                            hv = fma(v[a] * dphi[m], u, hv);
+                        }
+                }
+            }
+            h.out[((int64_t)i * d + j) * N + s] = hv;
+            h.out[((int64_t)j * d + i) * N + s] = hv;
+#pragma unroll
+            for (int b = 0; b < RB; b++) v[b] = nv[b];
+        }
+    }
+}
+
 // Deterministic block sum: warp shuffles, then warp partials combined in warp order.
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
 #pragma unroll
@@ -418,6 +500,21 @@ int launch_residual(const Inputs& in, int j, const double* core, int rl, int rr,
 
 int launch_sum_partials(const double* partial, int n_partials, int64_t stride, int n_elems, double* out, cudaStream_t st) {
     k_sum_partials<<<(n_elems + 127) / 128, 128, 0, st>>>(partial, n_partials, stride, n_elems, out);
+    BSDE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_hessian_row(const Inputs& in, int i, const double* cores, const int64_t* core_off, const int* ranks_dev,
+                       const double* const* rbond_dev, const double* Lin, int max_rank, double* out, cudaStream_t st) {
+    if (in.p > kMaxP || max_rank > 8) return fail_msg(2, "hessian: p = %d / rank %d outside the supported range", in.p, max_rank);
+    HessArgs h{cores, core_off, ranks_dev, rbond_dev, Lin, out, i};
+    const int grid = (int)std::min<int64_t>((in.N + kThreads - 1) / kThreads, 148 * 8);
+    const bool p4 = in.p <= 4;
+    if (max_rank <= 4) {
+        if (p4) k_hessian_row<4, 4><<<grid, kThreads, 0, st>>>(in, h); else k_hessian_row<4, 8><<<grid, kThreads, 0, st>>>(in, h);
+    } else {
+        if (p4) k_hessian_row<8, 4><<<grid, kThreads, 0, st>>>(in, h); else k_hessian_row<8, 8><<<grid, kThreads, 0, st>>>(in, h);
+    }
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -14,6 +14,8 @@ int launch_tt_eval(const Inputs& in, const double* cores, const int64_t* core_of
                    double* out, cudaStream_t st);
 int launch_grad_step(const Inputs& in, int i, const double* core, int rl, int rr, const double* Lin, const double* Rin,
                      double* Lout, double* z, cudaStream_t st);
+int launch_hessian_row(const Inputs& in, int i, const double* cores, const int64_t* core_off, const int* ranks_dev,
+                       const double* const* rbond_dev, const double* Lin, int max_rank, double* out, cudaStream_t st);
 int residual_grid(int64_t N);
 int launch_residual(const Inputs& in, int j, const double* core, int rl, int rr, const double* Lin, const double* Rin,
                     const double* y, double* pred_out, double* partial, double* out_sum, cudaStream_t st);

@@ -29,8 +29,8 @@ class DeviceInputs:
     kind BASIS_PHI: `data` is PHI [d][p][N] (and `ddata` the derivative values), the reference's explicit lists.
     """
 
-    def __init__(self, kind, p, data, ddata=None, coef=None):
-        self.kind, self.p, self.data, self.ddata = int(kind), int(p), data, ddata
+    def __init__(self, kind, p, data, ddata=None, coef=None, d2data=None):
+        self.kind, self.p, self.data, self.ddata, self.d2data = int(kind), int(p), data, ddata, d2data
         self.coef = None if coef is None else np.ascontiguousarray(coef, dtype=np.float64)
         self.d = int(data.shape[0])
         self.N = int(data.shape[-1])
@@ -210,6 +210,18 @@ class Backend:
         out = self.empty(inp.d, inp.N) if out is None else out
         self._call(self.lib.bsde_tt_grad, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.ddata),
                                     _ptr(inp.coef), _ptr(_i32(ranks)), _ptr(_f64(cores_flat)), _ptr(out))
+        return out
+
+    def tt_hessian(self, inp: DeviceInputs, ranks, cores_flat, out=None):
+        out = self.empty(inp.d, inp.d, inp.N) if out is None else out
+        self._call(self.lib.bsde_tt_hessian, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.ddata), _ptr(inp.d2data),
+                                       _ptr(inp.coef), _ptr(_i32(ranks)), _ptr(_f64(cores_flat)), _ptr(out))
+        return out
+
+    def tt_hessian(self, inp: DeviceInputs, ranks, cores_flat, out=None):
+        out = self.empty(inp.d, inp.d, inp.N) if out is None else out
+        self._call(self.lib.bsde_tt_hessian, inp.kind, inp.d, inp.p, inp.N, _ptr(inp.data), _ptr(inp.ddata), _ptr(inp.d2data),
+                                       _ptr(inp.coef), _ptr(_i32(ranks)), _ptr(_f64(cores_flat)), _ptr(out))
         return out
 
     # ---- paths, targets ----------------------------------------------------------------------------------

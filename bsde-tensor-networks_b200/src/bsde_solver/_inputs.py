@@ -64,11 +64,12 @@ def tagged_points(phis):
     return kind, p, coef, [t[3] for t in tags]
 
 
-def as_inputs(phis, dphis=None) -> DeviceInputs:
+def as_inputs(phis, dphis=None, ddphis=None) -> DeviceInputs:
     """DeviceInputs are passed through; host lists are stacked and uploaded (explicit-values mode)."""
     if isinstance(phis, DeviceInputs):
         return phis
     be = get_backend()
     host = stack_phis(phis)
     ddata = None if dphis is None else be.to_device(stack_phis(dphis))
-    return DeviceInputs(BASIS_PHI, host.shape[1], be.to_device(host), ddata=ddata)
+    d2data = None if ddphis is None else be.to_device(stack_phis(ddphis))
+    return DeviceInputs(BASIS_PHI, host.shape[1], be.to_device(host), ddata=ddata, d2data=d2data)

@@ -47,6 +47,7 @@ SIGNATURES = {
                        C.c_double, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp],
     "bsde_tt_eval": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp],
     "bsde_tt_grad": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "bsde_tt_hessian": [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "bsde_paths_simulate": [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, C.c_double, _vp, C.c_uint64, _i64, C.c_int, _vp, _vp],
     "bsde_terminal": [_vp, C.c_int, _vp, C.c_int, _i64, _vp, _vp],
     "bsde_target": [_vp, C.c_int, _vp, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, _vp],

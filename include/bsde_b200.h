@@ -135,6 +135,13 @@ BSDE_API int bsde_tt_grad(bsde_ctx* ctx, int basis_kind, int d, int p, int64_t N
                  const double* dphi_dev, const double* coef_host, const int* ranks, const double* cores_host,
                  double* z_out_dev);
 
+/* Hessian of the train at every sample (replaces hessian, core/calculus/hessian.py:6-26): h_out_dev [d][d][N], both
+ * triangles.  dphi_dev / d2phi_dev: PHI mode only (first / second derivative values [d][p][N]).  The reference contracts
+ * the whole network once per index pair, O(d^3) work; here one right-interface pass and one row kernel per asset, O(d^2). */
+BSDE_API int bsde_tt_hessian(bsde_ctx* ctx, int basis_kind, int d, int p, int64_t N, const double* inputs_dev, const double* dphi_dev,
+                    const double* d2phi_dev, const double* coef_host, const int* ranks, const double* cores_host,
+                    double* h_out_dev);
+
 /* ---- paths and targets   (replace generate_trajectories stochastic/path.py:6-34 and the target lines of
  *      src/scripts/pipeline.py:129-133, src/scripts/pipeline_explicit.py:97-102) ---------------------------- */
 /* x_out_dev [steps+1][d][N]; xi_dev [steps+1][d][N] is read when replay != 0 (host-supplied increments),

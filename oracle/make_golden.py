@@ -286,6 +286,32 @@ def golden_explicit_small():
     print("explicit small Y0", Y[:, 0].mean())
 
 
+def golden_hessian():
+    """hessian() of the reference (core/calculus/hessian.py:6-26) at a batch of points and at a single point, for a random
+    train in monomials and in Legendre polynomials; used by the parity tests of bsde_tt_hessian."""
+    from bsde_solver.core.calculus.hessian import hessian
+
+    np.random.seed(77)
+    N, d, r = 40, 5, 3
+    out = {"x": np.random.randn(N, d) * 0.8}
+    for name, basis in (("poly", PolynomialBasis(4)), ("leg", LegendreBasis(3))):
+        p = basis.degree
+        tt = TensorTrain([p] * d, (1,) + (r,) * (d - 1) + (1,))
+        tt.randomize()
+        out.update(pack(f"cores_{name}_", cores_of(tt)))
+        x = out["x"]
+        H = hessian(tt, make_phis(x, basis), make_phis(x, basis, "grad"), make_phis(x, basis, "dgrad"), batch=True)
+        out[f"H_{name}"] = np.array(H)
+        def single(kind, k=3):
+            f = getattr(basis, kind)
+            return [TensorCore(f(x[k:k + 1, i])[0], name=f"phi_{i+1}", indices=(f"m_{i+1}",)) for i in range(d)]
+        out[f"H1_{name}"] = np.array(hessian(tt, single("eval"), single("grad"), single("dgrad"), batch=False))
+        out[f"p_{name}"] = p
+    np.savez_compressed(os.path.join(OUT, "hessian.npz"), **out)
+    print("hessian fixture: batch", out["H_poly"].shape, "single", out["H1_poly"].shape,
+          "consistent", np.abs(out["H_poly"][:, :, 3] - out["H1_poly"]).max())
+
+
 def golden_pipeline_c2():
     """BASELINE config 2: Black-Scholes basket, d = 10, N = 2^16 paths, rank 2, 3 monomials, 50 steps, explicit ALS with
     10 sweeps per fit — the loop of src/scripts/pipeline.py:84-141 driven by the reference's own functions (the script's
@@ -332,5 +358,6 @@ if __name__ == "__main__":
     golden_salsa()
     golden_paths()
     golden_explicit_small()
+    golden_hessian()
     golden_pipeline_c1()
     print("done ->", OUT)

@@ -178,6 +178,25 @@ def tt_grad(cores, phis, dphis):
     return out
 
 
+def tt_hessian(cores, phis, dphis, ddphis):
+    """hessian (core/calculus/hessian.py:6-26) with batch=True: H[i, j, s] = the train contracted with the basis values of
+    every asset except i and j, which get the first-derivative values (i != j) or asset i the second-derivative values."""
+    d = len(cores)
+    N = phis[0].shape[0]
+    G = [core_times_phi(cores[k], phis[k]) for k in range(d)]         # (N, r, r')
+    dG = [core_times_phi(cores[k], dphis[k]) for k in range(d)]
+    ddG = [core_times_phi(cores[k], ddphis[k]) for k in range(d)]
+    H = np.zeros((d, d, N))
+    for i in range(d):
+        for j in range(i, d):
+            v = np.ones((N, 1))
+            for k in range(d):
+                M = ddG[k] if (k == i and k == j) else (dG[k] if k in (i, j) else G[k])
+                v = np.einsum("sa,sab->sb", v, M)
+            H[i, j] = H[j, i] = v[:, 0]
+    return H
+
+
 # --------------------------------------------------------------------------------------
 # small dense solve — core/optimisation/solve.py:6-19
 # --------------------------------------------------------------------------------------

@@ -293,3 +293,74 @@ def test_philox_stream_matches_the_restated_generator(backend):
     _, xi = backend.paths_simulate(1, np.array([1.0]), np.zeros(d), N, steps, 1.0, seed=(5 << 32) + 12345, sample_offset=1 << 33)
     ref = O.philox_increments((5 << 32) + 12345, N, d, steps, sample_offset=1 << 33)
     np.testing.assert_allclose(xi.cpu().numpy(), ref, rtol=0, atol=5e-15)
+
+
+# ---------------------------------------------------------------------------------------------- Hessian, PDE residual
+@pytest.mark.parametrize("name", ["poly", "leg"])
+def test_hessian_matches_reference(backend, golden, name):
+    """bsde_tt_hessian against the reference's hessian() (core/calculus/hessian.py:6-26): fused bases from x, the reference's
+    calling convention (lists of basis / derivative / second-derivative values, batch=True and a single point)."""
+    from bsde_solver.core.calculus.basis import LegendreBasis, PolynomialBasis
+    from bsde_solver.core.calculus.hessian import hessian
+    from bsde_solver.core.tensor.tensor_core import TensorCore
+    from bsde_solver.core.tensor.tensor_train import TensorTrain
+
+    g = golden("hessian.npz")
+    x = g["x"]
+    N, d = x.shape
+    p = int(g[f"p_{name}"])
+    cores = cores_from(g, f"cores_{name}_")
+    basis = PolynomialBasis(p) if name == "poly" else LegendreBasis(p)
+    tt = TensorTrain([p] * d, ranks_of(cores).tolist())
+    for i, c in enumerate(cores):
+        tt.cores[f"core_{i}"] = TensorCore.like(c, tt.cores[f"core_{i}"])
+    Hd = hessian(tt, basis.device_inputs(backend.to_device(np.ascontiguousarray(x.T)))).cpu().numpy()
+    assert rel(Hd, g[f"H_{name}"]) < 1e-13
+    lists = [[TensorCore(f(x[:, i]), name=f"phi_{i+1}", indices=("batch", f"m_{i+1}")) for i in range(d)] for f in (basis.eval, basis.grad, basis.dgrad)]
+    assert rel(hessian(tt, *lists, batch=True), g[f"H_{name}"]) < 1e-13
+    one = [[f(x[3:4, i])[0] for i in range(d)] for f in (basis.eval, basis.grad, basis.dgrad)]
+    assert rel(hessian(tt, *one, batch=False), g[f"H1_{name}"]) < 1e-13
+
+
+def test_pde_loss_vanishes_on_the_exact_solution(backend):
+    """PDELoss (loss.py:10-33) on the closed-form Black-Scholes-Barenblatt solution v = exp((r + sigma^2)(T - t)) |x|^2
+    (bsde.py:54-55): the residual d_t v + 1/2 Tr(sigma sigma^T D^2 v) + h must vanish; with the Hessian of a train that
+    represents |x|^2 exactly (rank 2, 3 monomials) it does to rounding."""
+    from bsde_solver.bsde import BlackScholes
+    from bsde_solver.core.calculus.basis import PolynomialBasis
+    from bsde_solver.core.calculus.derivative import multi_derivative
+    from bsde_solver.core.calculus.hessian import hessian
+    from bsde_solver.core.tensor.tensor_train import TensorTrain
+    from bsde_solver.loss import PDELoss
+    from bsde_solver.utils import fast_contract
+
+    rng = np.random.RandomState(1)
+    N, d, p = 300, 4, 3
+    x = 0.5 + rng.rand(N, d)
+    r, sig, T, t = 0.05, 0.4, 1.0, 0.3
+    model = BlackScholes(x[:1], 0.02, T, r, sig)
+    # |x|^2 as a rank-2 train: core_k carries (running sum, 1)
+    cores = []
+    for k in range(d):
+        rl, rr = (1 if k == 0 else 2), (1 if k == d - 1 else 2)
+        c = np.zeros((rl, p, rr))
+        if k == 0:
+            c[0, 2, 0], c[0, 0, 1] = 1.0, 1.0            # (x^2, 1)
+        elif k == d - 1:
+            c[0, 0, 0], c[1, 2, 0] = 1.0, 1.0            # sum + x^2
+        else:
+            c[0, 0, 0], c[1, 2, 0], c[1, 0, 1] = 1.0, 1.0, 1.0
+        cores.append(c)
+    tt = TensorTrain.from_tensor(np.zeros([p] * d), [1] + [2] * (d - 1) + [1]) if False else TensorTrain([p] * d, [1] + [2] * (d - 1) + [1])
+    from bsde_solver.core.tensor.tensor_core import TensorCore
+    for i, c in enumerate(cores):
+        tt.cores[f"core_{i}"] = TensorCore.like(c, tt.cores[f"core_{i}"])
+    inp = PolynomialBasis(p).device_inputs(backend.to_device(np.ascontiguousarray(x.T)))
+    scale = np.exp((r + sig**2) * (T - t))
+    v = scale * fast_contract(tt, inp).cpu().numpy()
+    np.testing.assert_allclose(v, scale * (x**2).sum(axis=1), rtol=1e-13)
+    vx = scale * multi_derivative(tt, inp).cpu().numpy().T
+    vxx = scale * hessian(tt, inp).cpu().numpy().transpose(2, 0, 1)
+    vt = -(r + sig**2) * v
+    loss = PDELoss(model)(t, x, v, vt, vx, vxx)
+    assert np.abs(loss).max() < 1e-12 * np.abs(v).max()

@@ -182,3 +182,16 @@ def test_philox_stream_properties():
     # known answer for Philox4x32-10 (Random123 kat_vectors: counter = key = 0)
     out = O._philox4x32_10(np.zeros((1, 4), dtype=np.uint64), 0, 0)[0]
     assert [int(v) for v in out] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_hessian_against_reference(golden):
+    """hessian() of the reference (core/calculus/hessian.py:6-26), batch and single point, monomials and Legendre."""
+    g = golden("hessian.npz")
+    x = g["x"]
+    d = x.shape[1]
+    for name, ev, gr, dg in (("poly", O.poly_eval, O.poly_grad, O.poly_dgrad), ("leg", O.legendre_eval, O.legendre_grad, O.legendre_dgrad)):
+        p = int(g[f"p_{name}"])
+        cores = cores_from(g, f"cores_{name}_")
+        H = O.tt_hessian(cores, [ev(x[:, i], p) for i in range(d)], [gr(x[:, i], p) for i in range(d)], [dg(x[:, i], p) for i in range(d)])
+        assert rel(H, g[f"H_{name}"]) < 1e-13
+        assert rel(H[:, :, 3], g[f"H1_{name}"]) < 1e-13
