@@ -67,6 +67,28 @@ k_interface_left(Inputs in, int j, const double* __restrict__ core, int r_in, in
 #pragma unroll
             for (int b = 0; b < RB; b++) acc[u][b] = 0.0;
         }
+        if (r_in == RB && r_out == RB && p == PB) {
+            // full shape (the interior cores of a uniform train): straight-line code, the core read as 16-byte broadcasts
+            // (half the shared-memory instructions; same order of the FMAs as the general form, hence the same bits)
+            const double2* c2 = reinterpret_cast<const double2*>(csm);
+#pragma unroll
+            for (int a = 0; a < RB; a++)
+#pragma unroll
+                for (int m = 0; m < PB; m++) {
+                    double t[kSB];
+#pragma unroll
+                    for (int u = 0; u < kSB; u++) t[u] = lall[u][a] * phi[u][m];
+#pragma unroll
+                    for (int b = 0; b < RB; b += 2) {
+                        const double2 cv = c2[((a * PB + m) * RB + b) >> 1];
+#pragma unroll
+                        for (int u = 0; u < kSB; u++) {
+                            acc[u][b] = fma(t[u], cv.x, acc[u][b]);
+                            acc[u][b + 1] = fma(t[u], cv.y, acc[u][b + 1]);
+                        }
+                    }
+                }
+        } else {
 #pragma unroll
         for (int a = 0; a < RB; a++) {
             if (a >= r_in) break;
@@ -86,6 +108,7 @@ k_interface_left(Inputs in, int j, const double* __restrict__ core, int r_in, in
                         }
                 }
             }
+        }
         }
 #pragma unroll
         for (int u = 0; u < kSB; u++) {
@@ -122,6 +145,42 @@ k_interface_right(Inputs in, int j, const double* __restrict__ core, int r_out, 
         }
 #pragma unroll
         for (int u = 0; u < kSB; u++) basis_values<PB>(in, j, sidx[u], 0, phi[u]);
+        if (r_in == RB && r_out == RB && p == PB) {
+            // full shape: straight-line code, 16-byte core reads, all RB outputs kept in registers and stored at the end
+            const double2* c2 = reinterpret_cast<const double2*>(csm);
+            double out[kSB][RB];
+#pragma unroll
+            for (int a = 0; a < RB; a++) {
+                double acc[kSB];
+#pragma unroll
+                for (int u = 0; u < kSB; u++) acc[u] = 0.0;
+#pragma unroll
+                for (int m = 0; m < PB; m++) {
+                    double t[kSB];
+#pragma unroll
+                    for (int u = 0; u < kSB; u++) t[u] = 0.0;
+#pragma unroll
+                    for (int b = 0; b < RB; b += 2) {
+                        const double2 cv = c2[((a * PB + m) * RB + b) >> 1];
+#pragma unroll
+                        for (int u = 0; u < kSB; u++) { t[u] = fma(cv.x, rb[u][b], t[u]); t[u] = fma(cv.y, rb[u][b + 1], t[u]); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kSB; u++) acc[u] = fma(phi[u][m], t[u], acc[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kSB; u++) out[u][a] = acc[u];
+            }
+#pragma unroll
+            for (int u = 0; u < kSB; u++) {
+                const int64_t s = s0 + u * stride;
+                if (s < N) {
+#pragma unroll
+                    for (int a = 0; a < RB; a++) Rout[(int64_t)a * N + s] = out[u][a];
+                }
+            }
+            continue;
+        }
         for (int a = 0; a < r_out; a++) {
             double acc[kSB];
 #pragma unroll
