@@ -307,24 +307,24 @@ def host_list_leg(be, torch, xT, y, ranks, init):
     return out
 
 
-def multi_gpu_check(be, torch, dist, rank, world, local, N_check=1 << 18, sweeps=6):
+def multi_gpu_check(be, torch, dist, rank, world, local, N_check=1 << 17, sweeps=6):
     """What tests/multigpu_check.py asserts, inside the driver-visible run: every rank ends a sharded fit with bit-identical
     cores, and that fit equals the single-GPU fit of the union of the shards (fresh single-GPU context on rank 0).  Run on
-    the converging workload's law (Black-Scholes, d = CONV_D): on the C3 throughput data the fit explains nothing
-    (residual 0.9995) and its cores are not a function of the data to any useful accuracy."""
+    a well-posed fit (HJB law with sigma = 0.6, d = 12, C3 core shape): on the C3 throughput data the fit explains nothing
+    (residual 0.9995) and on the converging workload most systems are rank-deficient — in both the cores are not a function
+    of the data to better than the fit residual, whatever the summation order."""
     from bsde_solver._backend import BASIS_POLY, Backend, DeviceInputs
 
-    d = CONV_D
-    par = np.array([0.05, 0.4])
-    x0 = np.tile([1.0, 0.5], d // 2)
-    rng = np.random.RandomState(5)
+    d = 12
+    sig = np.array([0.6])
+    rng = np.random.RandomState(3)
     ranks = np.array([1] + [R] * (d - 1) + [1], dtype=np.int32)
     init = np.concatenate([(rng.rand(ranks[i] * P * ranks[i + 1]) - 0.5) * 2 for i in range(d)])
 
     def data(b, lo, n):
-        x, _ = b.paths_simulate(0, par, x0, n, 10, 1.0, seed=909, sample_offset=lo, keep_xi=False)
-        xT = x[10].contiguous()
-        return xT, b.terminal(0, par, xT)
+        x, _ = b.paths_simulate(1, sig, np.zeros(d), n, 1, 1.0, seed=77, sample_offset=lo, keep_xi=False)
+        xT = x[1].contiguous()
+        return xT, b.terminal(1, sig, xT)
 
     xs, ys = data(be, rank * N_check, N_check)
     cores = init.copy()
@@ -346,7 +346,7 @@ def multi_gpu_check(be, torch, dist, rank, world, local, N_check=1 << 18, sweeps
         res = float(torch.linalg.vector_norm(f_shard - yu) / torch.linalg.vector_norm(yu))
     dist.barrier()
     return {"replicas_identical": identical, "vs_single_gpu": err, "fit_relative_residual": res,
-            "what": f"{sweeps}-sweep fit (Black-Scholes law d={d}, rank {R}, {P} monomials) on 2^{int(np.log2(N_check))} samples per rank: cores "
+            "what": f"{sweeps}-sweep fit (HJB law sigma=0.6, d={d}, rank {R}, {P} monomials) on 2^{int(np.log2(N_check))} samples per rank: cores "
                     "all-gathered and compared bit for bit; fitted values of the sharded fit vs the single-GPU fit of the union of the shards (relative L2)"}
 
 
