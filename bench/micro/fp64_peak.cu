@@ -94,7 +94,9 @@ float time_it(F launch) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     launch(); launch();
-    cudaDeviceSynchronize();
+    // a configuration the device cannot launch (too many registers for the block size) must not be reported as a rate
+    // (round 1 printed 239328 TFLOP/s for the 32-warp x 4-CTA rows: the launch had failed and the events timed nothing)
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { cudaGetLastError(); return -1.0f; }
     float best = 1e30f;
     for (int r = 0; r < 5; r++) {
         cudaEventRecord(e0);
@@ -104,6 +106,7 @@ float time_it(F launch) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
+    if (cudaGetLastError() != cudaSuccess) return -1.0f;
     return best;
 }
 
@@ -119,31 +122,41 @@ int main() {
         int blocks = sms * 4;
         double nthreads = (double)threads * blocks;
         float ms = time_it([&] { k_dfma<<<blocks, threads>>>(out, 1.0000001, 1e-9); });
-        printf("warps/CTA %2d x4 CTA/SM  DFMA           %8.2f TFLOP/s\n", wps, 2.0 * 16 * ITERS * nthreads / ms / 1e9);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("warps/CTA %2d x4 CTA/SM  DFMA           %8.2f TFLOP/s\n", wps, 2.0 * 16 * ITERS * nthreads / ms / 1e9);
         double nwarps = nthreads / 32;
         ms = time_it([&] { k_dmma884<8><<<blocks, threads>>>(out, 1.0000001, 1e-9); });
-        printf("warps/CTA %2d x4 CTA/SM  DMMA m8n8k4    %8.2f TFLOP/s\n", wps, 2.0 * 8 * 8 * 4 * 8 * ITERS * nwarps / ms / 1e9);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("warps/CTA %2d x4 CTA/SM  DMMA m8n8k4    %8.2f TFLOP/s\n", wps, 2.0 * 8 * 8 * 4 * 8 * ITERS * nwarps / ms / 1e9);
         ms = time_it([&] { k_dmma16<8, 4, 0><<<blocks, threads>>>(out, 1.0000001, 1e-9); });
-        printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k4   %8.2f TFLOP/s\n", wps, 2.0 * 16 * 8 * 4 * 8 * ITERS * nwarps / ms / 1e9);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k4   %8.2f TFLOP/s\n", wps, 2.0 * 16 * 8 * 4 * 8 * ITERS * nwarps / ms / 1e9);
         ms = time_it([&] { k_dmma16<8, 8, 0><<<blocks, threads>>>(out, 1.0000001, 1e-9); });
-        printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k8   %8.2f TFLOP/s\n", wps, 2.0 * 16 * 8 * 8 * 8 * ITERS * nwarps / ms / 1e9);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k8   %8.2f TFLOP/s\n", wps, 2.0 * 16 * 8 * 8 * 8 * ITERS * nwarps / ms / 1e9);
         ms = time_it([&] { k_dmma16<8, 16, 0><<<blocks, threads>>>(out, 1.0000001, 1e-9); });
-        printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k16  %8.2f TFLOP/s\n", wps, 2.0 * 16 * 8 * 16 * 8 * ITERS * nwarps / ms / 1e9);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k16  %8.2f TFLOP/s\n", wps, 2.0 * 16 * 8 * 16 * 8 * ITERS * nwarps / ms / 1e9);
         ms = time_it([&] { k_dmma16<8, 4, 8><<<blocks, threads>>>(out, 1.0000001, 1e-9); });
-        printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k4 + 8 DMUL per 8 DMMA: DMMA-only rate %8.2f TFLOP/s (time %.3f ms)\n", wps,
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k4 + 8 DMUL per 8 DMMA: DMMA-only rate %8.2f TFLOP/s (time %.3f ms)\n", wps,
                2.0 * 16 * 8 * 4 * 8 * ITERS * nwarps / ms / 1e9, ms);
         ms = time_it([&] { k_dmma16<8, 4, 32><<<blocks, threads>>>(out, 1.0000001, 1e-9); });
-        printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k4 + 32 DMUL per 8 DMMA: DMMA-only rate %8.2f TFLOP/s (time %.3f ms)\n", wps,
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("warps/CTA %2d x4 CTA/SM  DMMA m16n8k4 + 32 DMUL per 8 DMMA: DMMA-only rate %8.2f TFLOP/s (time %.3f ms)\n", wps,
                2.0 * 16 * 8 * 4 * 8 * ITERS * nwarps / ms / 1e9, ms);
     }
     // single-accumulator latency (dependent chain), 1 warp per SMSP
     {
         float ms = time_it([&] { k_dmma16<1, 4, 0><<<sms, 128>>>(out, 1.0000001, 1e-9); });
-        printf("dependent DMMA m16n8k4 chain: %.1f ns per mma (~%.0f cycles at 1.9 GHz)\n", ms * 1e6 / ITERS, ms * 1e6 / ITERS * 1.9);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("dependent DMMA m16n8k4 chain: %.1f ns per mma (~%.0f cycles at 1.9 GHz)\n", ms * 1e6 / ITERS, ms * 1e6 / ITERS * 1.9);
         ms = time_it([&] { k_dmma16<1, 8, 0><<<sms, 128>>>(out, 1.0000001, 1e-9); });
-        printf("dependent DMMA m16n8k8 chain: %.1f ns per mma\n", ms * 1e6 / ITERS);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("dependent DMMA m16n8k8 chain: %.1f ns per mma\n", ms * 1e6 / ITERS);
         ms = time_it([&] { k_dmma884<1><<<sms, 128>>>(out, 1.0000001, 1e-9); });
-        printf("dependent DMMA m8n8k4 chain: %.1f ns per mma\n", ms * 1e6 / ITERS);
+        if (ms < 0.0f) { printf("(launch failed: configuration not launchable on this device)\n"); }
+        if (ms > 0.0f) printf("dependent DMMA m8n8k4 chain: %.1f ns per mma\n", ms * 1e6 / ITERS);
     }
     cudaFree(out);
     return 0;
