@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbsde_b200.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["api.cu", "assembly.cu", "dense.cu", "interface.cu", "model.cu", "salsa.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "bsde_b200.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "vh_lstsq.cuh", os.path.join("..", "..", "include", "bsde_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden"]
