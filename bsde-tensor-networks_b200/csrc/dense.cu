@@ -1288,7 +1288,19 @@ k_micro_solve_fast(MicroSolveArgs a) {
         __syncthreads();
         __shared__ int s_sweeps;
         const SystemMatrix Amat{nullptr, stage, map, has_diagonal_terms(a) ? dg : nullptr, n, 1.0};      // stage is normalised already
-        int rank = vh_lstsq<kFastThreads, 8, 4>(Amat, n, bv, xs, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
+        VhScratch vhs = vh_carve(sm, n);
+#ifdef VH_PROFILE      // measurement build: phase cycles of the truncated solve into slots 16.. of the clock buffer
+        __shared__ long long s_vhclk[16];
+        if (tid < 16) s_vhclk[tid] = 0;
+        __syncthreads();
+        vhs.clk = a.clk ? s_vhclk : nullptr;
+        const long long vh_t0 = clock64();
+#endif
+        int rank = vh_lstsq<kFastThreads, 8, 4>(Amat, n, bv, xs, vhs, a.clk ? &s_sweeps : nullptr);
+#ifdef VH_PROFILE
+        if (a.clk && tid < 14) atomicAdd((unsigned long long*)(a.clk + 16 + tid), (unsigned long long)s_vhclk[tid]);
+        if (a.clk && tid == 0) atomicAdd((unsigned long long*)(a.clk + 31), (unsigned long long)(clock64() - vh_t0));
+#endif
         if (rank < 0) {                       // moments that are not a Gram matrix (overflow, NaN): no answer
             for (int i = tid; i < n; i += kFastThreads) xs[i] = nan("");
             rank = 0;

@@ -27,7 +27,7 @@
 namespace bsde {
 
 #ifdef VH_PROFILE
-#define VH_T(idx) do { if (threadIdx.x == 0) { const long long _n = clock64(); S.clk[idx] += _n - vh_t; vh_t = _n; } } while (0)
+#define VH_T(idx) do { if (threadIdx.x == 0 && S.clk) { const long long _n = clock64(); S.clk[idx] += _n - vh_t; vh_t = _n; } } while (0)
 #else
 #define VH_T(idx) do { } while (0)
 #endif
@@ -236,7 +236,120 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
     const double thr2 = 1e-14;                                    // another sweep when some cos^2 > thr2 (cos 1e-7: the
                                                                   // sweep leaves cos^2 ~ 1e-28 behind, quadratic convergence)
     int sweep = 0;
-    if (r > 1) {
+    // Jacobi rotation that orthogonalises two columns with squared norms al, be and inner product ga; w = be - al, g = 2 ga,
+    // hyp = sqrt(w^2 + g^2):  tan = sign(w) g / (|w| + hyp),  cos^2 = (|w| + hyp) / (2 hyp),  sin = sign(w) g / (2 hyp cos)
+    // — two reciprocal square roots and no division on the dependent chain.  w and g are first scaled by a power of two
+    // near 1 / max(al, be), so that the squares neither overflow nor vanish.
+    auto rotation = [](double al, double be, double ga, double& c, double& sn) {
+        const int ex = (__double2hiint(fmax(al, be)) >> 20) & 0x7ff;
+        const double scale = __hiloint2double((2046 - ex) << 20, 0);      // 2^(1023 - ex)
+        const double w = (be - al) * scale, g = 2.0 * ga * scale;
+        const double qq = fma(w, w, g * g);
+        const double rs = vh_rsqrt(qq);
+        const double hyp = qq * rs;
+        const double den = fabs(w) + hyp;
+        const double u2 = 0.5 * den * rs;                     // cos^2 in [1/2, 1]
+        const double rc = vh_rsqrt(u2);
+        c = u2 * rc;
+        sn = copysign(0.5 * g * rs, g * w) * rc;              // sign(w) g: w = 0 counts as positive
+    };
+#ifndef VH_FORCE_ROUND_ROBIN
+#define VH_FORCE_ROUND_ROBIN 0     // 1: always the round-robin tournament (A/B measurement)
+#endif
+    if (r > 1 && (r >> 1) <= PG && !VH_FORCE_ROUND_ROBIN) {
+        // ---- odd-even (Brent-Luk) ordering, one column per lane group resident in registers ----
+        // Group i owns slot 2i+1 for the whole phase (K, in registers).  Even rounds pair it with slot 2i, odd rounds with
+        // slot 2i+2; after the rotation the two columns trade places (the one from shared memory stays in the registers,
+        // the old K goes to the slot), so that every column travels through the array and meets every other one once in r
+        // rounds — the systolic-array ordering.  A round reads ONE column per pair from shared memory and writes one
+        // (the round-robin tournament below moves both: 64 KB per round at n = 64, the floor of that formulation), touches
+        // only the slot between two neighbouring groups, and needs one barrier.
+        const int ng = r >> 1;
+        const bool mine = pg < ng;
+        double2 kc[UMAX];
+        {
+            const double2* ck = reinterpret_cast<const double2*>(G + (size_t)(mine ? 2 * pg + 1 : 0) * ldg);
+#pragma unroll
+            for (int u = 0; u < UMAX; u++) {
+                const int c = pl + LP * u;
+                kc[u] = (mine && c < nchunk) ? ck[c] : make_double2(0.0, 0.0);
+            }
+        }
+        if (tid == 0) { S.flags[0] = 0; S.flags[1] = 0; }
+        __syncthreads();
+        for (; sweep < 30; sweep++) {
+            if (tid == 0) S.flags[(sweep + 1) & 1] = 0;
+            for (int t = 0; t < r; t++) {
+                const bool odd = (t & 1) != 0;
+                const int slot = 2 * pg + (odd ? 2 : 0);
+                const bool act = mine && slot < r;
+                VH_T(1);
+                // (every lane runs the same instruction stream with the full shuffle mask — idle groups work on zeros —
+                // so that the four groups of a warp never serialise)
+                double2* cx = reinterpret_cast<double2*>(G + (size_t)(act ? slot : 0) * ldg);
+                double2 xc[UMAX];
+#pragma unroll
+                for (int u = 0; u < UMAX; u++) {
+                    const int c = pl + LP * u;
+                    xc[u] = (act && c < nchunk) ? cx[c] : make_double2(0.0, 0.0);
+                }
+                double al0 = 0.0, be0 = 0.0, ga0 = 0.0, al1 = 0.0, be1 = 0.0, ga1 = 0.0;      // al: x.x, be: k.k
+#pragma unroll
+                for (int u = 0; u < UMAX; u++) {
+                    al0 = fma(xc[u].x, xc[u].x, al0); al1 = fma(xc[u].y, xc[u].y, al1);
+                    be0 = fma(kc[u].x, kc[u].x, be0); be1 = fma(kc[u].y, kc[u].y, be1);
+                    ga0 = fma(xc[u].x, kc[u].x, ga0); ga1 = fma(xc[u].y, kc[u].y, ga1);
+                }
+                double al = al0 + al1, be = be0 + be1, ga = ga0 + ga1;
+                VH_T(2);
+#pragma unroll
+                for (int o = LP >> 1; o > 0; o >>= 1) {
+                    al += __shfl_xor_sync(full, al, o);
+                    be += __shfl_xor_sync(full, be, o);
+                    ga += __shfl_xor_sync(full, ga, o);
+                }
+                VH_T(3);
+                // even round: x is the left column, K the right one; odd round: the mirror image.  Rotated columns
+                // left' = c left - s right, right' = s left + c right; then the two trade places: the registers keep what was
+                // read from the slot, the slot receives the old K.
+                double c = 1.0, sn = 0.0;
+                if (act && !(al <= negl && be <= negl)) {
+                    const double g2 = ga * ga, ab = al * be;
+                    if (g2 > thr2 * ab && pl == 0) S.flags[sweep & 1] = 1;
+                    if (g2 > tol2 * ab) rotation(odd ? be : al, odd ? al : be, ga, c, sn);
+                }
+                VH_T(4);
+                const double sx = odd ? -sn : sn;
+#pragma unroll
+                for (int u = 0; u < UMAX; u++) {
+                    const int cidx = pl + LP * u;
+                    const double2 x = xc[u], k = kc[u];
+                    // even: x' = c x - s k, k' = s x + c k;  odd: k' = c k - s x, x' = s k + c x
+                    const double2 xn = make_double2(fma(c, x.x, -sx * k.x), fma(c, x.y, -sx * k.y));
+                    const double2 kn = make_double2(fma(sx, x.x, c * k.x), fma(sx, x.y, c * k.y));
+                    if (act) {
+                        kc[u] = xn;
+                        if (cidx < nchunk) cx[cidx] = kn;
+                    }
+                }
+                VH_T(5);
+                __syncthreads();
+                VH_T(6);
+            }
+            const int need = S.flags[sweep & 1];
+            __syncthreads();                           // the flag is cleared again at the start of the next sweep
+            if (!need) { sweep++; break; }
+        }
+        if (mine) {
+            double2* ck = reinterpret_cast<double2*>(G + (size_t)(2 * pg + 1) * ldg);
+#pragma unroll
+            for (int u = 0; u < UMAX; u++) {
+                const int c = pl + LP * u;
+                if (c < nchunk) ck[c] = kc[u];
+            }
+        }
+        __syncthreads();
+    } else if (r > 1) {
         // the tournament's pairs, once per solve: tab[step * NP + k] = p | q << 8 (q = 255: padding of an odd r)
         unsigned short* tab = S.tab;
         for (int e = tid; e < (m - 1) * NP; e += T) {
@@ -284,21 +397,8 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
                     const double g2 = ga * ga, ab = al * be;
                     if (g2 > thr2 * ab && pl == 0) S.flags[sweep & 1] = 1;
                     if (g2 > tol2 * ab) {
-                        // Jacobi rotation that orthogonalises the two columns, with w = be - al, g = 2 ga, hyp = sqrt(w^2 + g^2):
-                        //   tan = sign(w) g / (|w| + hyp),  cos^2 = (|w| + hyp) / (2 hyp),  sin = sign(w) g / (2 hyp cos)
-                        // — two reciprocal square roots and no division on the dependent chain.  w and g are first scaled by
-                        // a power of two near 1 / max(al, be), so that the squares neither overflow nor vanish.
-                        const int ex = (__double2hiint(fmax(al, be)) >> 20) & 0x7ff;
-                        const double scale = __hiloint2double((2046 - ex) << 20, 0);      // 2^(1023 - ex)
-                        const double w = (be - al) * scale, g = 2.0 * ga * scale;
-                        const double qq = fma(w, w, g * g);
-                        const double rs = vh_rsqrt(qq);
-                        const double hyp = qq * rs;
-                        const double den = fabs(w) + hyp;
-                        const double u2 = 0.5 * den * rs;                     // cos^2 in [1/2, 1]
-                        const double rc = vh_rsqrt(u2);
-                        const double c = u2 * rc;
-                        const double s = copysign(0.5 * g * rs, g * w) * rc;  // sign(w) g: w = 0 counts as positive
+                        double c, s;
+                        rotation(al, be, ga, c, s);
                         VH_T(4);
 #pragma unroll
                         for (int u = 0; u < UMAX; u++) {
