@@ -95,11 +95,12 @@ struct bsde_ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     int64_t launches = 0;
     int64_t use_graph = 1;
-    DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg, clk;
+    DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg, clk, hints;
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
     int64_t solve_stop = 0;       // measurement only (MicroSolveArgs::stop_after)
     int64_t red_groups = 3;       // option: row groups of the moment reduction on a single GPU (1 = one level; measured best: 3)
+    int64_t solve_hints = 1;      // option: per-core "last solve truncated" hints (MicroSolveArgs::hint)
     int64_t gate_tier2 = 1;       // option: second-tier acceptance test in k_micro_solve_fast (MicroSolveArgs::tier2)
     int64_t svd_onesided = 0;     // A/B measurement: one-sided Jacobi SVD for symmetric systems too (MicroSolveArgs::force_onesided)
     int64_t fast_solve = 1;       // option: register-resident fast kernel in front of k_micro_solve (dense.cu)
@@ -338,6 +339,7 @@ struct MicroCtx {
     int solver;
     int mono;
     int* info;
+    int* hints = nullptr;      // one int per core (MicroSolveArgs::hint), zeroed at the start of the fit; ALS only
 };
 
 // assembly + (all-reduce) + solve/QR of core j; direction as MicroSolveArgs
@@ -400,6 +402,7 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     }
     if (sr) { a.eta_ptr = sr->eta; a.gamma = sr->gamma; a.theta = sr->theta; a.reg_left = sr->reg_left; a.reg_right = sr->reg_right; }
     if (c->fast_solve && c->scalars.p) a.fast_flag = c->scalars.as<int>() + 24;
+    if (m.hints && !sr && c->solve_hints) a.hint = m.hints + j;
     a.stop_after = (int)c->solve_stop;
     a.force_onesided = (int)c->svd_onesided;
     a.tier2 = (int)c->gate_tier2;
@@ -531,6 +534,9 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
         for (int j = 0; j < c->in_ev_count; j++) BSDE_CUDA_OK(cudaStreamWaitEvent(c->stream, c->in_ev[j], 0));
         c->in_ev_count = 0;
         MicroCtx m{&T, &in, &B, y_dev, solver_id, basis_kind == BASIS_POLY ? 1 : 0, info};
+        BSDE_TRY(c->hints.ensure(sizeof(int) * (size_t)d));
+        BSDE_CUDA_OK(cudaMemsetAsync(c->hints.p, 0, sizeof(int) * (size_t)d, c->stream));
+        m.hints = c->hints.as<int>();
         int it = 0;
         const int fused = (c->fuse_interface && basis_kind != BASIS_PHI) ? 1 : 0;
         if (n_iter > 0) { BSDE_TRY(als_sweep(c, m, fused, 1)); it = 1; }     // also builds the assembly plans / workspaces
@@ -755,7 +761,7 @@ int bsde_ctx_destroy(bsde_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto& kv : c->plans) asm_plan_free(kv.second);
-    for (DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg})
+    for (DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg, &c->hints})
         b->release();
     for (void* q : c->px_opened) if (q) cudaIpcCloseMemHandle(q);
     if (c->px_data_local) cudaFree(c->px_data_local);
@@ -800,6 +806,7 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     if (name && !strcmp(name, "solve_stop")) { c->solve_stop = value; return 0; }
     if (name && !strcmp(name, "svd_onesided")) { c->svd_onesided = value; return 0; }
     if (name && !strcmp(name, "gate_tier2")) { c->gate_tier2 = value; return 0; }
+    if (name && !strcmp(name, "solve_hints")) { c->solve_hints = value; return 0; }
     if (name && !strcmp(name, "r4_full")) { g_asm_r4_full = value ? 1 : 0; return 0; }
     if (name && !strcmp(name, "red_groups")) { if (value < 1 || value > kRedGroups) return fail_msg(2, "red_groups outside 1..%d", kRedGroups); c->red_groups = value; return 0; }
     if (name && !strcmp(name, "asm_generic")) {

@@ -1163,6 +1163,11 @@ k_micro_solve_fast(MicroSolveArgs a) {
     // vh_lstsq below, in this kernel (round 1 launched k_micro_solve behind every fast kernel for that: a 3 us no-op
     // launch per micro-step, and a 1.3 ms two-sided Jacobi when it was needed).
     bool accepted = s_red[1] == 0.0;
+    // *a.hint != 0: the last solve of this core truncated (set below; cleared at the start of every fit).  The systems of
+    // a core stay rank-deficient from sweep to sweep once the fit has converged, so the factorisation and its acceptance
+    // tests (~35k cycles) are not tried again — vh_lstsq returns lstsq's answer whatever the conditioning, and clears the
+    // hint again when it finds the system comfortably regular.  (uniform: one word read by every thread)
+    if (a.hint && *a.hint != 0) accepted = false;
     BSDE_PHASE(0);
     long long t_sub = t_phase;
     if (a.stop_after == 1) return;
@@ -1263,7 +1268,11 @@ k_micro_solve_fast(MicroSolveArgs a) {
     {
         const double zz = s_red[2];
         bool ok = isfinite(zz) && zz > 0.0 && sqrt((double)n / zz) / s_red[0] > kGateSafety * DBL_EPSILON * (double)n;
-        if (!ok && isfinite(zz) && zz > 0.0 && a.tier2) {
+        // Hopeless systems skip the second tier (~45k cycles on one warp): cond >= (trace / n) / sigma_min, so when the
+        // bound on sigma_min is below eps / 4 of the trace lstsq truncates whatever the better estimates say (its threshold
+        // is cond = 1 / (eps n)) — the systems of a converged fit with excess rank sit at 1e-17 .. 1e-20.
+        const bool hopeless = !(sqrt((double)n / zz) / s_red[0] > 0.25 * DBL_EPSILON);
+        if (!ok && isfinite(zz) && zz > 0.0 && a.tier2 && !hopeless) {
             // ---- second tier.  The first test is cheap but loose (trace >= sigma_max by up to n, one probe solve, safety
             // 100): at N >= 2^21 samples a tenth of the C3 micro-steps fail it although lstsq truncates nothing (measured:
             // cond 10^12.4 .. 10^13.6 against the truncation threshold 1/(eps n) = 10^13.85), and each of them costs an
@@ -1309,6 +1318,8 @@ k_micro_solve_fast(MicroSolveArgs a) {
         if (tid == 0) {
             if (a.info) { atomicAdd(a.info + 1, 1); atomicMin(a.info + 3, rank); }
             if (a.clk) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
+            // regular with a margin of 1000 over lstsq's cutoff: the next solve of this core tries the factorisation again
+            if (a.hint) *a.hint = (rank == n && vhs.red[4] > 1e3) ? 0 : 1;
         }
     }
     BSDE_PHASE(1);

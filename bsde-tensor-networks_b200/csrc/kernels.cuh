@@ -111,6 +111,7 @@ struct MicroSolveArgs {
     int force_onesided = 0;             // A/B measurement: symmetric systems also take the one-sided Jacobi SVD (option "svd_onesided")
     int stop_after = 0;                 // measurement only: k_micro_solve_fast returns after phase 1 (load), 2 (factor), 3 (solve)
     int* fast_flag = nullptr;           // device int: enables k_micro_solve_fast (written 0 = done, 1 = fallback needed)
+    int* hint = nullptr;                // device int of this core: != 0 = its last solve truncated (k_micro_solve_fast goes straight to vh_lstsq)
     const double* A_direct = nullptr;   // explicit n x n system (then rl = n, p = rr = 1 and moments is unused)
     const double* b_direct = nullptr;
 };

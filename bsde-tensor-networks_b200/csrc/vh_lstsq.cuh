@@ -133,6 +133,108 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
     auto make_key = [](double v, int i) -> long long {
         return v > 0.0 ? ((__double_as_longlong(v) & ~0xffll) | (long long)(255 - i)) : LLONG_MIN;
     };
+    int r = 0;
+#ifndef VH_FORCE_LEFT_LOOKING
+#define VH_FORCE_LEFT_LOOKING 0     // 1: always the left-looking factorisation (A/B measurement)
+#endif
+    if (T == 256 && n <= 64 && !VH_FORCE_LEFT_LOOKING) {
+        // ---- right-looking, register-resident: the Schur complement lives in 4 x 4 blocks on a 16 x 16 thread grid ----
+        // Per step: every warp finds the pivot among the 64 diagonal entries (its own register copy, two warp-wide integer
+        // maxima), the 16 threads that hold column jk publish it, ONE barrier, every thread scales its 4 + 4 entries of the
+        // column and updates its 16 entries.  ~700 cycles per step against ~1500 of the left-looking form below (dot products over the k finished columns from shared memory,
+        // two shuffle reductions, per-warp pivot keys), which stays for other thread counts and n > 64.
+        const int ty = tid >> 4, tx = tid & 15;
+        double Sr[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int i = 4 * ty + a, j = 4 * tx + b;
+                Sr[a][b] = (i < n && j < n) ? Aat(i, j) : 0.0;
+            }
+        // the pivot column of the step, double-buffered by step parity (S.coef and S.lam are free until the final phase), so
+        // that one barrier per step is enough; every warp keeps its own copy of the diagonal (lane l: rows l, l + 32) and
+        // updates it from the published column with the very operations of the diagonal blocks — no second exchange
+        double* colbuf[2] = {S.coef, S.lam};
+        unsigned long long sel = 0ull;                 // rows already selected
+        double dd0 = lane < n ? d[lane] : -DBL_MAX, dd1 = lane + 32 < n ? d[lane + 32] : -DBL_MAX;
+        for (int k = 0; k < n; k++) {
+            VH_T(8);
+            // pivot = largest remaining diagonal entry (ties: lowest row).  The 64-bit keys (value bits with the row in the
+            // lowest 8) are compared as two 32-bit halves, each with one warp-wide integer maximum (REDUX)
+            int jk;
+            {
+                const long long k0 = make_key(dd0, lane), k1 = make_key(dd1, lane + 32);
+                const long long km = k0 > k1 ? k0 : k1;
+                if (__all_sync(full, km == LLONG_MIN)) break;                 // nothing positive left (uniform over the CTA)
+                const unsigned hi = km == LLONG_MIN ? 0u : (unsigned)(km >> 32), lo = (unsigned)km;
+                const unsigned himax = __reduce_max_sync(full, hi);
+                const unsigned lomax = __reduce_max_sync(full, (km != LLONG_MIN && hi == himax) ? lo : 0u);
+                jk = 255 - (int)(lomax & 0xffu);
+            }
+            VH_T(9);
+            double* cb_ = colbuf[k & 1];
+            if (tx == (jk >> 2)) {
+                const int cb = jk & 3;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+                    if (4 * ty + a < n) cb_[4 * ty + a] = cb == 0 ? Sr[a][0] : (cb == 1 ? Sr[a][1] : (cb == 2 ? Sr[a][2] : Sr[a][3]));
+            }
+            __syncthreads();
+            VH_T(10);
+            const double bv = cb_[jk];                 // the pivot itself: entry jk of its own column
+            if (!(bv > tolpiv)) break;
+            const double inv = vh_rsqrt(bv), lkk = bv * inv;
+            sel |= 1ull << jk;
+            double li[4], lj[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int i = 4 * ty + a, j = 4 * tx + a;
+                li[a] = (i < n && !((sel >> i) & 1ull)) ? cb_[i] * inv : 0.0;
+                lj[a] = (j < n && !((sel >> j) & 1ull)) ? cb_[j] * inv : 0.0;
+            }
+            {   // this warp's copy of the diagonal
+                const double l0 = lane < n ? cb_[lane] * inv : 0.0, l1 = lane + 32 < n ? cb_[lane + 32] * inv : 0.0;
+                dd0 = (lane >= n || ((sel >> lane) & 1ull)) ? -DBL_MAX : fma(-l0, l0, dd0);
+                dd1 = (lane + 32 >= n || ((sel >> (lane + 32)) & 1ull)) ? -DBL_MAX : fma(-l1, l1, dd1);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) Sr[a][b] = fma(-li[a], lj[b], Sr[a][b]);
+            VH_T(11);
+            if (tx == 0) {
+                double* colk = G + (size_t)k * ldg;
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    const int i = 4 * ty + a;
+                    if (i < n) colk[i] = (i == jk) ? lkk : li[a];
+                }
+            }
+            VH_T(12);
+            r = k + 1;
+        }
+        __syncthreads();
+        if (warp == 0) {                               // what the final phase and the caller read: selected rows marked in d
+            if (lane < n) d[lane] = dd0;
+            if (lane + 32 < n) d[lane + 32] = dd1;
+        }
+        if (r < n) {       // positive semi-definite to working accuracy?  what is left of the Schur complement must be noise
+            if (tid == 0) S.flags[2] = 0;
+            __syncthreads();
+            bool bad = false;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int i = 4 * ty + a, j = 4 * tx + b;
+                    if (i < n && j <= i && !((sel >> i) & 1ull) && !((sel >> j) & 1ull) && !(fabs(Sr[a][b]) <= 1e-10 * dmax0)) bad = true;
+                }
+            if (bad) S.flags[2] = 1;
+            __syncthreads();
+            if (S.flags[2]) return -1;
+        }
+    } else {
     {   // keys of the initial diagonal
         long long key = LLONG_MIN;
         for (int i0 = warp * RPW; i0 < n; i0 += nwarps * RPW) {
@@ -144,7 +246,6 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
         if (lane == 0) S.keys[warp] = key;
     }
     __syncthreads();
-    int r = 0;
     for (int k = 0; k < n; k++) {
         VH_T(8);
         long long key = lane < nwarps ? S.keys[(k & 1) * 32 + lane] : LLONG_MIN;
@@ -218,6 +319,7 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
         if (bad) S.flags[2] = 1;
         __syncthreads();
         if (S.flags[2]) return -1;
+    }
     }
     if (r == 0) {                                      // A = 0: the minimum-norm solution is 0
         for (int i = tid; i < n; i += T) xout[i] = 0.0;
@@ -449,9 +551,14 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
     for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(full, lmax, o));
     const double cutoff = DBL_EPSILON * (double)n * lmax;
     int rank = 0;
-    for (int i = lane; i < r; i += 32) rank += (S.lam[i] > cutoff) ? 1 : 0;
+    double lmin = DBL_MAX;                              // smallest eigenvalue that is kept
+    for (int i = lane; i < r; i += 32) {
+        const double l = S.lam[i];
+        if (l > cutoff) { rank++; lmin = fmin(lmin, l); }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(full, rank, o);
+    for (int o = 16; o > 0; o >>= 1) { rank += __shfl_xor_sync(full, rank, o); lmin = fmin(lmin, __shfl_xor_sync(full, lmin, o)); }
+    if (tid == 0) S.red[4] = cutoff > 0.0 ? lmin / cutoff : 0.0;     // margin of the rank decision, for the caller
     __syncthreads();
     for (int i = tid; i < r; i += T) {
         const double l = S.lam[i];
