@@ -207,6 +207,50 @@ def test_fast_solve_kernel_matches_the_general_one(backend):
         assert rel(fits[1], ref) < 1e-9, (ranks, rel(fits[1], ref))
 
 
+def test_truncated_solves_inside_a_converging_fit(backend):
+    """A train with more rank than the target needs (y = |x|^2 has TT rank 2, the train rank 4): once the fit converges most
+    normal equations are numerically rank-deficient and numpy.linalg.lstsq truncates.  k_micro_solve_fast then runs
+    vh_lstsq (right-looking pivoted Cholesky + odd-even Jacobi) and, with the per-core hints, skips the factorisation the
+    next time the core comes up.  Asserted: the fit reaches the target as the numpy oracle does; hints on / off and the
+    general kernel (left-looking factorisation, same Jacobi) give the same fitted values to rounding amplified by the
+    truncation; truncated solves were actually taken; repeated runs give the same bits."""
+    import oracle.tt_oracle as O
+    from bsde_solver._backend import DeviceInputs
+    from bsde_solver._lib import BASIS_POLY
+
+    rng = np.random.RandomState(51)
+    d, p, N, sweeps = 6, 4, 1 << 13, 6
+    ranks = np.array([1] + [4] * (d - 1) + [1], dtype=np.int32)
+    x = np.tile([1.0, 0.5], d // 2) * np.exp(-0.03 + 0.4 * rng.randn(N, d))
+    y = (x**2).sum(axis=1)
+    init = [rng.rand(ranks[i], p, ranks[i + 1]) * 2 - 1 for i in range(d)]
+    phis = [O.poly_eval(x[:, i], p) for i in range(d)]
+    ref = O.tt_eval(O.als(phis, y, n_iter=sweeps, cores=[c.copy() for c in init], randomize=False), phis)
+    ref_res = rel(ref, y)
+    inp = DeviceInputs(BASIS_POLY, p, backend.to_device(np.ascontiguousarray(x.T)))
+    yd = backend.to_device(y)
+    fits, infos, cores = {}, {}, {}
+    try:
+        for key, (fast, hints) in {"hints": (1, 1), "no_hints": (1, 0), "general": (0, 1), "again": (1, 1)}.items():
+            backend.set_option("fast_solve", fast)
+            backend.set_option("solve_hints", hints)
+            got = flat(init)
+            infos[key] = backend.fit_als(inp, yd, sweeps, ranks, 0, got)
+            cores[key] = got
+            fits[key] = backend.tt_eval(inp, ranks, got).cpu().numpy()
+    finally:
+        backend.set_option("fast_solve", 1)
+        backend.set_option("solve_hints", 1)
+    assert infos["hints"][1] > 10 and infos["no_hints"][1] > 10, infos         # truncated solves taken
+    assert infos["hints"][1] >= infos["no_hints"][1], infos                    # hinted cores skip the factorisation
+    assert np.array_equal(cores["hints"], cores["again"])
+    res = rel(fits["hints"], y)
+    assert res < max(10 * ref_res, 1e-6), (res, ref_res)
+    for key in ("no_hints", "general"):
+        assert rel(fits[key], fits["hints"]) < max(1e-7, 10 * res), (key, rel(fits[key], fits["hints"]), res)
+    assert rel(fits["hints"], ref) < max(1e-7, 10 * max(res, ref_res)), (rel(fits["hints"], ref), res, ref_res)
+
+
 def test_step0_fit_returns_mean(backend):
     """at time step 0 all samples coincide, A has rank 1, lstsq's minimum-norm solution fits mean(y)."""
     from bsde_solver._backend import DeviceInputs
