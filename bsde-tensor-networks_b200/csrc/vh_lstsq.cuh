@@ -339,21 +339,23 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
                                                                   // sweep leaves cos^2 ~ 1e-28 behind, quadratic convergence)
     int sweep = 0;
     // Jacobi rotation that orthogonalises two columns with squared norms al, be and inner product ga; w = be - al, g = 2 ga,
-    // hyp = sqrt(w^2 + g^2):  tan = sign(w) g / (|w| + hyp),  cos^2 = (|w| + hyp) / (2 hyp),  sin = sign(w) g / (2 hyp cos)
-    // — two reciprocal square roots and no division on the dependent chain.  w and g are first scaled by a power of two
-    // near 1 / max(al, be), so that the squares neither overflow nor vanish.
+    // hyp = sqrt(w^2 + g^2), a = |w| + hyp:  tan = sign(w) g / a, so (cos, sin) = (a, sign(w) g) / sqrt(a^2 + g^2).
+    // The normalisation is done to full precision (one reciprocal square root with its correction step: the rotation is
+    // orthogonal to rounding), hyp only to the 2^-22 of the hardware seed: the angle is then off by 2^-22 relative, i.e. the
+    // rotation leaves 2^-22 of the inner product behind instead of nothing — far below what the next sweep removes, and
+    // the second correction step (60 cycles of the dependent chain of every round) is gone.  w and g are first scaled by a
+    // power of two near 1 / max(al, be), so that the squares neither overflow nor vanish.
     auto rotation = [](double al, double be, double ga, double& c, double& sn) {
         const int ex = (__double2hiint(fmax(al, be)) >> 20) & 0x7ff;
         const double scale = __hiloint2double((2046 - ex) << 20, 0);      // 2^(1023 - ex)
         const double w = (be - al) * scale, g = 2.0 * ga * scale;
         const double qq = fma(w, w, g * g);
-        const double rs = vh_rsqrt(qq);
-        const double hyp = qq * rs;
-        const double den = fabs(w) + hyp;
-        const double u2 = 0.5 * den * rs;                     // cos^2 in [1/2, 1]
-        const double rc = vh_rsqrt(u2);
-        c = u2 * rc;
-        sn = copysign(0.5 * g * rs, g * w) * rc;              // sign(w) g: w = 0 counts as positive
+        double seed;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(qq));
+        const double a = fma(qq, seed, fabs(w));             // |w| + hyp
+        const double rn = vh_rsqrt(fma(a, a, g * g));
+        c = a * rn;
+        sn = copysign(g * rn, g * w);                         // sign(w) g: w = 0 counts as positive
     };
 #ifndef VH_FORCE_ROUND_ROBIN
 #define VH_FORCE_ROUND_ROBIN 0     // 1: always the round-robin tournament (A/B measurement)
@@ -379,16 +381,19 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
         }
         if (tid == 0) { S.flags[0] = 0; S.flags[1] = 0; }
         __syncthreads();
+        // the slot this group works on in even / odd rounds
+        const bool act_odd = mine && 2 * pg + 2 < r;
+        double2* const cx_even = reinterpret_cast<double2*>(G + (size_t)(mine ? 2 * pg : 0) * ldg);
+        double2* const cx_odd = reinterpret_cast<double2*>(G + (size_t)(act_odd ? 2 * pg + 2 : 0) * ldg);
         for (; sweep < 30; sweep++) {
             if (tid == 0) S.flags[(sweep + 1) & 1] = 0;
             for (int t = 0; t < r; t++) {
                 const bool odd = (t & 1) != 0;
-                const int slot = 2 * pg + (odd ? 2 : 0);
-                const bool act = mine && slot < r;
+                const bool act = odd ? act_odd : mine;
                 VH_T(1);
                 // (every lane runs the same instruction stream with the full shuffle mask — idle groups work on zeros —
                 // so that the four groups of a warp never serialise)
-                double2* cx = reinterpret_cast<double2*>(G + (size_t)(act ? slot : 0) * ldg);
+                double2* cx = odd ? cx_odd : cx_even;
                 double2 xc[UMAX];
 #pragma unroll
                 for (int u = 0; u < UMAX; u++) {
