@@ -325,7 +325,7 @@ __device__ __forceinline__ void write_partials(const AsmArgs& a, double* sm, dou
 // resident CTAs per SM the register allocation is tuned for: 3 (168 registers).  With 4 (128 registers) the operand
 // look-ahead spills and the kernel is 30 % slower (measured at both 15 and 20 accumulator tiles).
 #ifndef BSDE_RB_MIN_BLOCKS
-#define BSDE_RB_MIN_BLOCKS(nt) 3
+#define BSDE_RB_MIN_BLOCKS(nt) ((nt) > 20 ? 2 : 3)      // 28 accumulator tiles (general basis at r = p = 4) need more than 168 registers
 #endif
 template <int RT1, int CT1, int RT2, int RB, int PB>
 __global__ void __launch_bounds__(kAsmThreads, BSDE_RB_MIN_BLOCKS(RT1 * CT1 + RT2))
@@ -825,7 +825,8 @@ int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, i
             case 3: return run_kernel(k_assemble_rb<4, 1, 2, RB, PB>, op, P, a, st, occ);
             case 4: return run_kernel(k_assemble_rb<5, 1, 2, RB, PB>, op, P, a, st, occ);
             case 5: return run_kernel(k_assemble_rb<13, 1, 2, RB, PB>, op, P, a, st, occ);
-            default: return run_kernel(k_assemble_rb<9, 2, 2, RB, PB>, op, P, a, st, occ);
+            case 6: return run_kernel(k_assemble_rb<9, 2, 2, RB, PB>, op, P, a, st, occ);
+            default: return run_kernel(k_assemble_rb<13, 2, 2, RB, PB>, op, P, a, st, occ);
         }
     }
     if (P.NJ == 4) return run_kernel(k_assemble<4, RB, PB>, op, P, a, st, occ);
@@ -843,8 +844,8 @@ int dispatch(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* o
 
 // tile-count classes of the register-blocked kernel: (row tiles of M1, column tiles of M1, row tiles of M2)
 // ordered by total tile count RT1*CT1 + RT2
-constexpr int kNumRbClasses = 7;
-const int kRbClasses[kNumRbClasses][3] = {{1, 1, 1}, {2, 1, 1}, {2, 2, 1}, {4, 1, 2}, {5, 1, 2}, {13, 1, 2}, {9, 2, 2}};
+constexpr int kNumRbClasses = 8;
+const int kRbClasses[kNumRbClasses][3] = {{1, 1, 1}, {2, 1, 1}, {2, 2, 1}, {4, 1, 2}, {5, 1, 2}, {13, 1, 2}, {9, 2, 2}, {13, 2, 2}};
 
 }  // namespace
 
