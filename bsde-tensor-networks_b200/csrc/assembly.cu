@@ -327,8 +327,18 @@ __device__ __forceinline__ void write_partials(const AsmArgs& a, double* sm, dou
 #ifndef BSDE_RB_MIN_BLOCKS
 #define BSDE_RB_MIN_BLOCKS(nt) ((nt) > 20 ? 2 : 3)      // 28 accumulator tiles (general basis at r = p = 4) need more than 168 registers
 #endif
-template <int RT1, int CT1, int RT2, int RB, int PB>
-__global__ void __launch_bounds__(kAsmThreads, BSDE_RB_MIN_BLOCKS(RT1 * CT1 + RT2))
+// Sections 3 and 4 (RT3 > 0) serve shapes whose column index is just above one tile wide — a general basis at r = p = 4
+// has nB = nLL = nRR = 10: rows (lambda, rho) x columns beta would need 13 x 2 tiles for 10 columns.  There the columns
+// beta >= 8 are turned into rows:   section 1  rows (lambda, rho)   x columns beta < 8      13 tiles
+//                                   section 3  rows (beta', lambda) x columns rho < 8        3 tiles   (beta' = beta - 8)
+//                                   section 4  rows (beta', rho')   x columns lambda         1 x 2 tiles (rho' = rho - 8)
+// 20 accumulator tiles with M2 instead of 28.  Table: rows1, cols1, rows2, cols2, rows3 [RT3][8][2], cols3 [8], rows4
+// [RT4][8][2], cols4 [CT4][8].
+#ifndef BSDE_RB_SECT_MIN_BLOCKS
+#define BSDE_RB_SECT_MIN_BLOCKS 2      // 19 row tiles of fragment sources + 20 accumulator tiles: 168 registers spill (measured: 167 vs 146 us)
+#endif
+template <int RT1, int CT1, int RT2, int RB, int PB, int RT3 = 0, int RT4 = 0, int CT4 = 1>
+__global__ void __launch_bounds__(kAsmThreads, RT3 > 0 ? BSDE_RB_SECT_MIN_BLOCKS : BSDE_RB_MIN_BLOCKS(RT1 * CT1 + RT2 + RT3 + RT4 * CT4))
 k_assemble_rb(AsmArgs a) {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -342,10 +352,12 @@ k_assemble_rb(AsmArgs a) {
     }
     __syncthreads();
     const int g8 = lane >> 2;
-    // per-lane fragment sources (offsets in doubles): row tiles of M1 then of M2, two factors each; column tiles
-    constexpr int RT = RT1 + RT2;
+    // per-lane fragment sources (offsets in doubles): row tiles of the sections in order 1, 2 (M2), 3, 4, two factors
+    // each; column tiles of every section
+    constexpr int RT = RT1 + RT2 + RT3 + RT4;
+    constexpr int CT4n = RT4 > 0 ? CT4 : 1;
     int rlo[RT], rhi[RT];
-    int colA[CT1], colB;
+    int colA[CT1], colB, colC = 0, colD[CT4n];
     {
         const unsigned short* t = stab;
 #pragma unroll
@@ -358,9 +370,19 @@ k_assemble_rb(AsmArgs a) {
         for (int r = 0; r < RT2; r++) { rlo[RT1 + r] = t[(r * 8 + g8) * 2]; rhi[RT1 + r] = t[(r * 8 + g8) * 2 + 1]; }
         t += RT2 * 16;
         colB = t[g8];
+        t += 8;
+#pragma unroll
+        for (int r = 0; r < RT3; r++) { rlo[RT1 + RT2 + r] = t[(r * 8 + g8) * 2]; rhi[RT1 + RT2 + r] = t[(r * 8 + g8) * 2 + 1]; }
+        if (RT3 > 0) { t += RT3 * 16; colC = t[g8]; t += 8; }
+#pragma unroll
+        for (int r = 0; r < RT4; r++) { rlo[RT1 + RT2 + RT3 + r] = t[(r * 8 + g8) * 2]; rhi[RT1 + RT2 + RT3 + r] = t[(r * 8 + g8) * 2 + 1]; }
+        if (RT4 > 0) t += RT4 * 16;
+#pragma unroll
+        for (int c = 0; c < CT4n; c++) colD[c] = RT4 > 0 ? t[c * 8 + g8] : 0;
     }
 
-    constexpr int NT = RT1 * CT1 + RT2;
+    constexpr int NT = RT1 * CT1 + RT2 + RT3 + RT4 * CT4;
+    constexpr int T2 = RT1 * CT1, T3 = T2 + RT2, T4 = T3 + RT3;      // first accumulator tile of sections 2, 3, 4
     double acc[NT][2];
 #pragma unroll
     for (int t = 0; t < NT; t++) acc[t][0] = acc[t][1] = 0.0;
@@ -385,10 +407,13 @@ k_assemble_rb(AsmArgs a) {
         double n1a = w[rlo[R2] + (RT > 2 ? 0 : 4)], n1b = w[rhi[R2] + (RT > 2 ? 0 : 4)];
 #pragma unroll 1
         for (int step = 0; step < 8; step++, w += 4) {
-            double bc[CT1];
+            double bc[CT1], bd[CT4n];
 #pragma unroll
             for (int c = 0; c < CT1; c++) bc[c] = w[colA[c]];
             const double b2 = w[colB];
+            const double b3 = RT3 > 0 ? w[colC] : 0.0;
+#pragma unroll
+            for (int c = 0; c < CT4n; c++) bd[c] = RT4 > 0 ? w[colD[c]] : 0.0;
 #pragma unroll
             for (int r = 0; r < RT; r++) {
                 const double cur = av;
@@ -403,8 +428,14 @@ k_assemble_rb(AsmArgs a) {
                 if (r < RT1) {
 #pragma unroll
                     for (int c = 0; c < CT1; c++) dmma884(acc[r * CT1 + c][0], acc[r * CT1 + c][1], cur, bc[c]);
+                } else if (r < RT1 + RT2) {
+                    dmma884(acc[T2 + (r - RT1)][0], acc[T2 + (r - RT1)][1], cur, b2);
+                } else if (r < RT1 + RT2 + RT3) {
+                    dmma884(acc[T3 + (r - RT1 - RT2)][0], acc[T3 + (r - RT1 - RT2)][1], cur, b3);
                 } else {
-                    dmma884(acc[RT1 * CT1 + (r - RT1)][0], acc[RT1 * CT1 + (r - RT1)][1], cur, b2);
+#pragma unroll
+                    for (int c = 0; c < CT4n; c++)
+                        dmma884(acc[T4 + (r - RT1 - RT2 - RT3) * CT4n + c][0], acc[T4 + (r - RT1 - RT2 - RT3) * CT4n + c][1], cur, bd[c]);
                 }
             }
         }
@@ -803,6 +834,7 @@ int run_kernel(K kernel, int op, const AsmPlan& plan, const AsmArgs* args, cudaS
 }
 
 constexpr int kRbClassR4 = 100;       // AsmPlan::rb_class of k_assemble_r4
+constexpr int kRbClassSectioned = 8;  // k_assemble_rb<13, 1, 2, RB, PB, 3, 1, 2>: columns beta >= 8 turned into rows (see the kernel)
 
 template <int RB, int PB>
 int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* occ) {
@@ -826,7 +858,8 @@ int dispatch_rbpb(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, i
             case 4: return run_kernel(k_assemble_rb<5, 1, 2, RB, PB>, op, P, a, st, occ);
             case 5: return run_kernel(k_assemble_rb<13, 1, 2, RB, PB>, op, P, a, st, occ);
             case 6: return run_kernel(k_assemble_rb<9, 2, 2, RB, PB>, op, P, a, st, occ);
-            default: return run_kernel(k_assemble_rb<13, 2, 2, RB, PB>, op, P, a, st, occ);
+            case 7: return run_kernel(k_assemble_rb<13, 2, 2, RB, PB>, op, P, a, st, occ);
+            default: return run_kernel(k_assemble_rb<13, 1, 2, RB, PB, 3, 1, 2>, op, P, a, st, occ);     // kRbClassSectioned
         }
     }
     if (P.NJ == 4) return run_kernel(k_assemble<4, RB, PB>, op, P, a, st, occ);
@@ -894,7 +927,61 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
         }
     }
 
-    if (use_r4) {
+    // sectioned layout (kRbClassSectioned): column index beta just above one tile wide — see k_assemble_rb
+    if (force_generic != 1 && !use_r4 && P.nB > 8 && P.nB <= 10 && P.nRR <= 10 && P.nLL <= 16 && P.nLL * P.nRR <= 104 &&
+        (P.nB - 8) * P.nLL <= 24 && rl * rr <= 16 && p <= 8) {
+        const int cur = P.rb_class >= 0 ? kRbClasses[P.rb_class][0] * kRbClasses[P.rb_class][1] + kRbClasses[P.rb_class][2] : (1 << 30);
+        if (20 < cur) P.rb_class = kRbClassSectioned;
+    }
+
+    if (P.rb_class == kRbClassSectioned) {
+        constexpr int RT1 = 13, RT2 = 2, RT3 = 3, CT4 = 2;
+        n_tiles = RT1 + RT2 + RT3 + CT4;
+        P.NJ = n_tiles; P.n_groups = 1; P.n_jobs = n_tiles;
+        tab.assign((size_t)RT1 * 16 + 8 + RT2 * 16 + 8 + RT3 * 16 + 8 + 16 + CT4 * 8, 0);      // 0 = the ZERO function
+        uint16_t* rows1t = tab.data();
+        uint16_t* cols1t = rows1t + RT1 * 16;
+        uint16_t* rows2t = cols1t + 8;
+        uint16_t* cols2t = rows2t + RT2 * 16;
+        uint16_t* rows3t = cols2t + 8;
+        uint16_t* cols3t = rows3t + RT3 * 16;
+        uint16_t* rows4t = cols3t + 8;
+        uint16_t* cols4t = rows4t + 16;
+        const int T2 = RT1, T3 = T2 + RT2, T4 = T3 + RT3;
+        const int nRlo = std::min(P.nRR, 8), nRx = P.nRR - nRlo;
+        for (int beta = 0; beta < P.nB; beta++)
+            for (int lam = 0; lam < P.nLL; lam++)
+                for (int rho = 0; rho < P.nRR; rho++) {
+                    int slot;
+                    if (beta < 8) {                       // section 1: rows (lambda, rho), column beta
+                        const int r = lam * P.nRR + rho;
+                        rows1t[r * 2] = (uint16_t)(P.fLL + lam); rows1t[r * 2 + 1] = (uint16_t)(P.fRR + rho);
+                        cols1t[beta] = (uint16_t)(P.fRow1 + beta);
+                        slot = (r / 8) * 64 + (r % 8) * 8 + beta;
+                    } else if (rho < 8) {                 // section 3: rows (beta', lambda), column rho
+                        const int r = (beta - 8) * P.nLL + lam;
+                        rows3t[r * 2] = (uint16_t)(P.fRow1 + beta); rows3t[r * 2 + 1] = (uint16_t)(P.fLL + lam);
+                        cols3t[rho] = (uint16_t)(P.fRR + rho);
+                        slot = (T3 + r / 8) * 64 + (r % 8) * 8 + rho;
+                    } else {                              // section 4: rows (beta', rho'), columns lambda
+                        const int r = (beta - 8) * nRx + (rho - 8);
+                        rows4t[r * 2] = (uint16_t)(P.fRow1 + beta); rows4t[r * 2 + 1] = (uint16_t)(P.fRR + rho);
+                        cols4t[lam] = (uint16_t)(P.fLL + lam);
+                        slot = (T4 + lam / 8) * 64 + r * 8 + lam % 8;
+                    }
+                    P.h_gather[((size_t)beta * P.nLL + lam) * P.nRR + rho] = slot;
+                }
+        for (int m = 0; m < p; m++)
+            for (int a = 0; a < rl; a++)
+                for (int b = 0; b < rr; b++) {
+                    const int r = a * rr + b;
+                    rows2t[r * 2] = (uint16_t)(P.fL + a); rows2t[r * 2 + 1] = (uint16_t)(P.fR + b);
+                    cols2t[m] = (uint16_t)(P.fRow2 + m);
+                    P.h_gather[base2 + ((size_t)m * rl + a) * rr + b] = (T2 + r / 8) * 64 + (r % 8) * 8 + m;
+                }
+        P.tab_entries = (int)tab.size();
+        tab_smem = tab.size() * sizeof(uint16_t);
+    } else if (use_r4) {
         // k_assemble_r4: see the tile layout in its header comment
         P.rb_class = kRbClassR4;
         n_tiles = kR4Tiles;

@@ -78,15 +78,30 @@ __device__ __forceinline__ void basis_from_x(const Inputs& in, double x, int der
         }
         return;
     }
-    // BASIS_LEGENDRE: numpy.polyval order — y = 0; for c in coeffs (descending): y = y*x + c   (basis.py:38-44)
+    // BASIS_LEGENDRE: numpy.polyval order — y = 0; for c in coeffs (descending): y = y*x + c   (basis.py:38-44).
+    // Two rows of coefficients are fetched at a time with every load issued before the first use, and the Horner chains of
+    // the two rows are interleaved: with the loads inside a run-time loop (round 1) every step of every chain waited for its
+    // own coefficient — ~95 us per assembly launch at the C3 shape for 64 multiply-adds per sample (ncu, round 2).  Same
+    // operations in the same order: bit-identical.
     const double* cf = in.coef + (int64_t)deriv * in.p * in.p;
+    const int p = in.p;
 #pragma unroll
-    for (int m = 0; m < PB; m++) {
-        double yv = 0.0;
-        if (m < in.p) {
-            for (int k = 0; k < in.p; k++) yv = __dadd_rn(__dmul_rn(yv, x), __ldg(cf + m * in.p + k));
+    for (int m0 = 0; m0 < PB; m0 += 2) {
+        double c0[PB], c1[PB];
+#pragma unroll
+        for (int k = 0; k < PB; k++) {
+            c0[k] = (m0 < p && k < p) ? __ldg(cf + m0 * p + k) : 0.0;
+            c1[k] = (m0 + 1 < PB && m0 + 1 < p && k < p) ? __ldg(cf + (m0 + 1) * p + k) : 0.0;
         }
-        phi[m] = yv;
+        double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < PB; k++)
+            if (k < p) {
+                y0 = __dadd_rn(__dmul_rn(y0, x), c0[k]);
+                y1 = __dadd_rn(__dmul_rn(y1, x), c1[k]);
+            }
+        phi[m0] = (m0 < p) ? y0 : 0.0;
+        if (m0 + 1 < PB) phi[m0 + 1] = (m0 + 1 < p) ? y1 : 0.0;
     }
 }
 
