@@ -130,8 +130,9 @@ __device__ __forceinline__ void fuse_interface(const AsmArgs& a, const double* _
     double out[RB];
     // full interior shape (monomials, p = PB, both bond ranks = RB): straight-line code, the core read as 16-byte
     // broadcasts — the C3 hot path; every other shape takes the predicated general form below
-    if (a.in.kind == BASIS_POLY && a.in.p == PB && a.fr_in == RB && (a.fuse == 1 ? a.rl : a.rr) == RB) {
-        monomials_cr<PB>(r.xf, phi);
+    if (a.in.kind != BASIS_PHI && a.in.p == PB && a.fr_in == RB && (a.fuse == 1 ? a.rl : a.rr) == RB) {
+        if (a.in.kind == BASIS_POLY) monomials_cr<PB>(r.xf, phi);
+        else basis_from_x<PB>(a.in, r.xf, 0, phi);
         const double2* c2 = reinterpret_cast<const double2*>(core);
         if (a.fuse == 1) {
 #pragma unroll
@@ -237,6 +238,42 @@ __device__ __forceinline__ double stage_functions(const AsmArgs& a, double* __re
     const double vm = r.vm;
     const double yv = r.y * vm;
     ws[lane] = 0.0;
+    if (a.rl == RB && a.rr == RB && a.in.p == PB && !a.mono) {
+        // full shape, general basis (Legendre in the kernel or explicit values): every slot index is a compile-time
+        // constant — the predicated form below spends ~400 integer / predicate instructions per 32-sample chunk on its
+        // run-time shape (ncu source page of k_assemble_rb at rank 2, round 2)
+        constexpr int nP = RB * (RB + 1) / 2, nBf = PB * (PB + 1) / 2;
+        constexpr int fLL = 1, fRR = fLL + nP, fRow1 = fRR + nP, fL = fRow1 + nBf, fR = fL + RB, fRow2 = fR + RB;
+        int idx = 0;
+#pragma unroll
+        for (int q = 0; q < RB; q++)
+#pragma unroll
+            for (int q2 = q; q2 < RB; q2++) {
+                ws[(fLL + idx) * kStride + lane] = r.L[q] * r.L[q2];
+                ws[(fRR + idx) * kStride + lane] = r.R[q] * r.R[q2];
+                idx++;
+            }
+#pragma unroll
+        for (int q = 0; q < RB; q++) {
+            ws[(fL + q) * kStride + lane] = r.L[q];
+            ws[(fR + q) * kStride + lane] = r.R[q];
+        }
+        double phi[PB];
+        if (a.in.kind == BASIS_PHI) {
+#pragma unroll
+            for (int m = 0; m < PB; m++) phi[m] = r.xb[m];
+        } else {
+            basis_from_x<PB>(a.in, r.xb[0], 0, phi);
+        }
+        idx = 0;
+#pragma unroll
+        for (int m = 0; m < PB; m++)
+#pragma unroll
+            for (int m2 = m; m2 < PB; m2++) { ws[(fRow1 + idx) * kStride + lane] = vm * phi[m] * phi[m2]; idx++; }
+#pragma unroll
+        for (int m = 0; m < PB; m++) ws[(fRow2 + m) * kStride + lane] = phi[m] * yv;
+        return yv * yv;
+    }
     {
         int idx = a.fLL;
 #pragma unroll
