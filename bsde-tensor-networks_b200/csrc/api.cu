@@ -642,11 +642,12 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
     bool expand_rank = false, has_adapted = false;
     const int warmup = 2;
     int last_adapt = 0, rank_limited = 0;
-    for (int it = 0; it < n_iter; it++) {
-        if (it >= last_adapt + warmup) expand_rank = true;                               // als.py:224
-        if (has_adapted) { expand_rank = false; has_adapted = false; last_adapt = it; }   // als.py:225
+    // one sweep, als.py:222-298 (everything a sweep launches; the host decisions about expand_rank stay in the loop below)
+    auto sweep = [&](int it) -> int {
         if (d >= 2) {
-            BSDE_CUDA_OK(cudaMemcpyAsync(T.ranks_dev, T.ranks.data(), sizeof(int) * (d + 1), cudaMemcpyHostToDevice, c->stream));
+            // (a captured sweep has fixed ranks: the device copy is refreshed once, before the capture)
+            if (!c->capturing)
+                BSDE_CUDA_OK(cudaMemcpyAsync(T.ranks_dev, T.ranks.data(), sizeof(int) * (d + 1), cudaMemcpyHostToDevice, c->stream));
             BSDE_TRY(launch_orthonormalize_right(T.cores, T.off_dev, T.ranks_dev, p, d, 1, d - 1, c->stream));   // als.py:234
             c->launches++;
             BSDE_TRY(build_right(c, T, in, B, 2));          // bond[k] = R_{k-1} for k >= 2 (R_0 is rebuilt at j = 0)
@@ -713,7 +714,70 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
             BSDE_TRY(launch_salsa_scalars(state, res_sum, n_total, freq_omega, 1, c->stream));
             c->launches++;
         }
+            return 0;
+    };
+    // A sweep in which no bond may grow launches a fixed sequence of kernels (no rank read-back): it is captured once
+    // into a CUDA graph and replayed for as long as that stays true and the ranks do not change — after the adaptations
+    // have saturated that is every remaining sweep of the fit (measured at C4, round 2: 285 us per micro-step of eager
+    // launches against ~150 us of kernel time).
+    cudaGraph_t sgraph = nullptr;
+    cudaGraphExec_t sexec = nullptr;
+    int64_t sgraph_launches = 0;
+    auto drop_graph = [&]() {
+        if (sexec) cudaGraphExecDestroy(sexec);
+        if (sgraph) cudaGraphDestroy(sgraph);
+        sexec = nullptr; sgraph = nullptr;
+    };
+    int rc_fit = 0;
+    for (int it = 0; it < n_iter && !rc_fit; it++) {
+        if (it >= last_adapt + warmup) expand_rank = true;                               // als.py:224
+        if (has_adapted) { expand_rank = false; has_adapted = false; last_adapt = it; }   // als.py:225
+        bool may_grow_any = false;
+        if (expand_rank)
+            for (int j = 1; j < d; j++) {
+                if (T.ranks[j] < max_ranks[j - 1] && T.ranks[j] >= kRankLimit) rank_limited = 1;
+                if (T.ranks[j] < max_ranks[j - 1] && T.ranks[j] < kRankLimit) may_grow_any = true;
+            }
+        const bool fixed = it > 0 && !may_grow_any && d >= 2 && c->use_graph && !c->profile;
+        if (!fixed) {
+            drop_graph();                                   // the ranks may change in this sweep
+            rc_fit = sweep(it);
+            continue;
+        }
+        if (!sexec) {
+            // nothing may allocate inside the capture: plans and workspaces of every core shape of the current ranks first
+            // (a bond that grew in the last eager sweep changed the shape of the core to its left after that core's turn)
+            BSDE_CUDA_OK(cudaMemcpyAsync(T.ranks_dev, T.ranks.data(), sizeof(int) * (d + 1), cudaMemcpyHostToDevice, c->stream));
+            BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+            for (int j = 0; j < d; j++) {
+                const AsmPlan* P;
+                BSDE_TRY(get_plan(c, T.ranks[j], p, T.ranks[j + 1], m.mono, N, &P));
+                BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
+                BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride * kRedGroups));
+            }
+            const int64_t before = c->launches;
+            BSDE_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            c->capturing = true;
+            const int rc = sweep(it);
+            c->capturing = false;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &sgraph);
+            if (rc) { drop_graph(); return rc; }
+            if (e != cudaSuccess) { drop_graph(); return fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__); }
+            sgraph_launches = c->launches - before;
+            c->launches = before;
+            e = cudaGraphInstantiate(&sexec, sgraph, 0);
+            if (e != cudaSuccess) { drop_graph(); return fail_cuda(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+        }
+        const cudaError_t e = cudaGraphLaunch(sexec, c->stream);
+        if (e != cudaSuccess) { drop_graph(); return fail_cuda(e, "cudaGraphLaunch", __FILE__, __LINE__); }
+        c->launches += sgraph_launches;
     }
+    if (sexec) {                                            // the graph reads host and device buffers of this fit
+        const cudaError_t e = cudaStreamSynchronize(c->stream);
+        drop_graph();
+        if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    if (rc_fit) return rc_fit;
     BSDE_TRY(train_download(c, T, cores_host));
     BSDE_TRY(px_check(c));
     for (int k = 0; k <= d; k++) ranks[k] = T.ranks[k];
