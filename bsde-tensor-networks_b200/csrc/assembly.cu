@@ -238,12 +238,12 @@ __device__ __forceinline__ double stage_functions(const AsmArgs& a, double* __re
     const double vm = r.vm;
     const double yv = r.y * vm;
     ws[lane] = 0.0;
-    if (a.rl == RB && a.rr == RB && a.in.p == PB && !a.mono) {
-        // full shape, general basis (Legendre in the kernel or explicit values): every slot index is a compile-time
-        // constant — the predicated form below spends ~400 integer / predicate instructions per 32-sample chunk on its
-        // run-time shape (ncu source page of k_assemble_rb at rank 2, round 2)
-        constexpr int nP = RB * (RB + 1) / 2, nBf = PB * (PB + 1) / 2;
-        constexpr int fLL = 1, fRR = fLL + nP, fRow1 = fRR + nP, fL = fRow1 + nBf, fR = fL + RB, fRow2 = fR + RB;
+    if (a.rl == RB && a.rr == RB && a.in.p == PB) {
+        // full shape: every slot index is a compile-time constant — the predicated form below spends ~400 integer /
+        // predicate instructions per 32-sample chunk on its run-time shape (ncu source page of k_assemble_rb at rank 2,
+        // round 2).  Same values into the same slots as the general form.
+        constexpr int nP = RB * (RB + 1) / 2;
+        constexpr int fLL = 1, fRR = fLL + nP, fRow1 = fRR + nP;
         int idx = 0;
 #pragma unroll
         for (int q = 0; q < RB; q++)
@@ -253,6 +253,24 @@ __device__ __forceinline__ double stage_functions(const AsmArgs& a, double* __re
                 ws[(fRR + idx) * kStride + lane] = r.R[q] * r.R[q2];
                 idx++;
             }
+        if (a.mono) {
+            constexpr int nBm = 2 * PB - 1, fL = fRow1 + nBm, fR = fL + RB, fRow2 = fR + RB;
+#pragma unroll
+            for (int q = 0; q < RB; q++) {
+                ws[(fL + q) * kStride + lane] = r.L[q];
+                ws[(fR + q) * kStride + lane] = r.R[q];
+            }
+            const double x = r.xb[0];
+            double pw = vm;
+#pragma unroll
+            for (int k = 0; k < nBm; k++) {
+                ws[(fRow1 + k) * kStride + lane] = pw;
+                if (k < PB) ws[(fRow2 + k) * kStride + lane] = pw * yv;
+                pw *= x;
+            }
+            return yv * yv;
+        }
+        constexpr int nBf = PB * (PB + 1) / 2, fL = fRow1 + nBf, fR = fL + RB, fRow2 = fR + RB;
 #pragma unroll
         for (int q = 0; q < RB; q++) {
             ws[(fL + q) * kStride + lane] = r.L[q];
@@ -908,6 +926,24 @@ int dispatch(int op, const AsmPlan& P, const AsmArgs* a, cudaStream_t st, int* o
     int rb = std::max(P.rl, P.rr);
     if (a && a->fuse) rb = std::max(rb, a->fr_in);      // the fused update holds the neighbouring bond in the same registers
     const bool p4 = P.p <= 4;
+    if (op == OP_OCCUPANCY) {
+        // a fused update from a wider neighbour pushes a launch into a wider instantiation: every instantiation this plan
+        // can reach gets its shared-memory attribute; the grid follows the occupancy of the narrowest one
+        int o2 = 0, o4 = 0, o8 = 0;
+        int rc = p4 ? dispatch_rbpb<8, 4>(op, P, a, st, &o8) : dispatch_rbpb<8, 8>(op, P, a, st, &o8);
+        if (rc) return rc;
+        if (rb <= 4) { rc = p4 ? dispatch_rbpb<4, 4>(op, P, a, st, &o4) : dispatch_rbpb<4, 8>(op, P, a, st, &o4); if (rc) return rc; }
+        if (rb <= 2) { rc = p4 ? dispatch_rbpb<2, 4>(op, P, a, st, &o2) : dispatch_rbpb<2, 8>(op, P, a, st, &o2); if (rc) return rc; }
+#ifdef BSDE_NO_RB2
+        if (rb <= 2) o2 = o4;
+#endif
+        *occ = rb <= 2 ? o2 : (rb <= 4 ? o4 : o8);
+        return 0;
+    }
+    // (rank <= 2 trains — SALSA starts there — have their own bound: the full-shape fast paths then apply at rank 2)
+#ifndef BSDE_NO_RB2
+    if (rb <= 2) return p4 ? dispatch_rbpb<2, 4>(op, P, a, st, occ) : dispatch_rbpb<2, 8>(op, P, a, st, occ);
+#endif
     if (rb <= 4) return p4 ? dispatch_rbpb<4, 4>(op, P, a, st, occ) : dispatch_rbpb<4, 8>(op, P, a, st, occ);
     return p4 ? dispatch_rbpb<8, 4>(op, P, a, st, occ) : dispatch_rbpb<8, 8>(op, P, a, st, occ);
 }
