@@ -20,6 +20,12 @@ for (rl, p, rr, spread) in [(4, 4, 4, 0.0), (4, 4, 4, 1.0), (4, 4, 4, 3.0), (2, 
     y = np.log(1 + np.sum(V[:, :3] ** 2, axis=1))
     A = V.T @ V
     out.append((0.5 * (A + A.T), V.T @ y))
+# cores of 65..128 unknowns (the reference's own benchmark point benchmark_cupy.py:28-36 is r = p = 5: n = 125)
+for (rl, p, rr, spread) in [(5, 5, 5, 0.0), (5, 5, 5, 1.5), (4, 6, 4, 0.5), (4, 8, 4, 0.3), (5, 3, 5, 1.0), (5, 5, 4, 0.5)]:
+    V = design(rl, p, rr, 2000, spread)
+    y = np.log(1 + np.sum(V[:, :3] ** 2, axis=1))
+    A = V.T @ V
+    out.append((0.5 * (A + A.T), V.T @ y))
 for n in (6, 16, 64):
     v = rng.randn(n); out.append((2000.0 * np.outer(v, v), 3.7 * v))
 M = rng.randn(18, 20); A = M.T @ M; out.append((A, A @ rng.randn(20)))

@@ -1422,7 +1422,12 @@ k_micro_solve(MicroSolveArgs a) {
                     for (int i = threadIdx.x; i < n; i += blockDim.x) S.sc[i] = regularised_diagonal(a, i, stage_buf[a.expand_map[i * n + i]]) * nrm;
                 __syncthreads();
                 const SystemMatrix Amat{a.A_direct, stage_buf, a.expand_map, diag ? S.sc : nullptr, n, nrm};
-                rank = vh_lstsq<kDenseThreads, 32, 3>(Amat, n, S.bvec, xtmp, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
+                // up to 128 unknowns: 16 lanes per column pair, i.e. 64 pairs at once — a whole round of the odd-even
+                // ordering with one column per lane group resident in registers (one pass, one barrier per round);
+                // beyond: 32 lanes per pair and the round-robin tournament in two passes per round
+                // (bench/micro/vh_solve.cu times both on cores of 65..128 unknowns)
+                if (n <= 128) rank = vh_lstsq<kDenseThreads, 16, 4>(Amat, n, S.bvec, xtmp, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
+                else rank = vh_lstsq<kDenseThreads, 32, 3>(Amat, n, S.bvec, xtmp, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
                 if (rank >= 0 && a.clk && threadIdx.x == 0) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
             }
             if (rank < 0) {

@@ -337,6 +337,15 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
     const double tol2 = DBL_EPSILON * DBL_EPSILON;               // rotate when cos^2 > tol2
     const double thr2 = 1e-14;                                    // another sweep when some cos^2 > thr2 (cos 1e-7: the
                                                                   // sweep leaves cos^2 ~ 1e-28 behind, quadratic convergence)
+    // ... unless BOTH columns of the pair lie below a quarter of the smallest possible truncation cutoff
+    // (eps n lambda_max >= eps n dmax0): such columns are dropped whatever their mutual angle (cos^2 <= thr2_sub = 1e-4
+    // bounds what any group of them could add up to far below the cutoff), and their entries are rounding noise of the
+    // large columns, so their angles never settle — on the heavily rank-deficient systems of small sample sets (the
+    // reference's benchmark point N = 2000, r = p = 5: numerical rank 26..66 of 125) a handful of such pairs kept the
+    // sweeps going up to the limit of 30 (7 with this rule; same ranks, solutions equal to 1e-11 in the fit seminorm:
+    // scratch/sweeps_r5.py).  They are still rotated like every other pair.
+    const double sub_cut = 0.25 * DBL_EPSILON * (double)n * dmax0;
+    const double thr2_sub = 1e-4;
     int sweep = 0;
     // Jacobi rotation that orthogonalises two columns with squared norms al, be and inner product ga; w = be - al, g = 2 ga,
     // hyp = sqrt(w^2 + g^2), a = |w| + hyp:  tan = sign(w) g / a, so (cos, sin) = (a, sign(w) g) / sqrt(a^2 + g^2).
@@ -422,7 +431,7 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
                 double c = 1.0, sn = 0.0;
                 if (act && !(al <= negl && be <= negl)) {
                     const double g2 = ga * ga, ab = al * be;
-                    if (g2 > thr2 * ab && pl == 0) S.flags[sweep & 1] = 1;
+                    if (g2 > ((al <= sub_cut && be <= sub_cut) ? thr2_sub : thr2) * ab && pl == 0) S.flags[sweep & 1] = 1;
                     if (g2 > tol2 * ab) rotation(odd ? be : al, odd ? al : be, ga, c, sn);
                 }
                 VH_T(4);
@@ -502,7 +511,7 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
                     VH_T(3);
                     if (!valid || (al <= negl && be <= negl)) continue;       // no shuffles below this line
                     const double g2 = ga * ga, ab = al * be;
-                    if (g2 > thr2 * ab && pl == 0) S.flags[sweep & 1] = 1;
+                    if (g2 > ((al <= sub_cut && be <= sub_cut) ? thr2_sub : thr2) * ab && pl == 0) S.flags[sweep & 1] = 1;
                     if (g2 > tol2 * ab) {
                         double c, s;
                         rotation(al, be, ga, c, s);
