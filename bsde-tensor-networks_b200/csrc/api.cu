@@ -96,6 +96,7 @@ struct bsde_ctx {
     int64_t launches = 0;
     int64_t use_graph = 1;
     DevBuf bond, partial, moments, cores, meta, coef, tmp, in_copy, y_copy, scalars, dbg, clk, hints;
+    DevBuf solve_ws;              // global-memory workspace of k_micro_solve for cores beyond its shared memory (dense.cu)
     std::map<std::tuple<int, int, int, int, int64_t>, AsmPlan> plans;
     int64_t asm_generic = 0;   // option: force the generic assembly kernel (A/B measurements, tests)
     int64_t solve_stop = 0;       // measurement only (MicroSolveArgs::stop_after)
@@ -406,6 +407,10 @@ int micro_step(bsde_ctx* c, const MicroCtx& m, int j, int direction, double ridg
     a.stop_after = (int)c->solve_stop;
     a.force_onesided = (int)c->svd_onesided;
     a.tier2 = (int)c->gate_tier2;
+    if (const size_t ws = micro_solve_workspace_bytes(rl * T.p * rr, a.n_slots)) {      // cores beyond the solver's shared memory
+        BSDE_TRY(c->solve_ws.ensure(ws));
+        a.big_ws = c->solve_ws.as<double>();
+    }
     int extra = 0;
     BSDE_TRY(launch_micro_solve(a, c->stream, &extra));
     c->launches += 1 + extra;
@@ -754,6 +759,7 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
                 BSDE_TRY(get_plan(c, T.ranks[j], p, T.ranks[j + 1], m.mono, N, &P));
                 BSDE_TRY(c->partial.ensure(sizeof(double) * (size_t)P->grid_x * P->partial_stride));
                 BSDE_TRY(c->moments.ensure(sizeof(double) * (size_t)P->partial_stride * kRedGroups));
+                BSDE_TRY(c->solve_ws.ensure(micro_solve_workspace_bytes(T.ranks[j] * p * T.ranks[j + 1], (int)P->partial_stride)));
             }
             const int64_t before = c->launches;
             BSDE_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -825,7 +831,7 @@ int bsde_ctx_destroy(bsde_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (auto& kv : c->plans) asm_plan_free(kv.second);
-    for (DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg, &c->hints})
+    for (DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg, &c->hints, &c->solve_ws})
         b->release();
     for (void* q : c->px_opened) if (q) cudaIpcCloseMemHandle(q);
     if (c->px_data_local) cudaFree(c->px_data_local);
@@ -910,7 +916,7 @@ int bsde_ctx_get_stat(bsde_ctx* c, const char* name, double* out) {
     if (!strcmp(name, "sm_count")) { *out = c->sm_count; return 0; }
     if (!strcmp(name, "workspace_bytes")) {
         double t = 0;
-        for (const DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg})
+        for (const DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg, &c->solve_ws})
             t += (double)b->cap;
         *out = t;
         return 0;

@@ -12,7 +12,8 @@ namespace bsde {
 
 constexpr int kMaxP = 8;        // basis functions per asset supported by the fused kernels
 constexpr int kMaxR = 16;       // TT rank supported by the fused kernels
-constexpr int kMaxN = 144;      // unknowns of one core (r*p*r) supported by the in-CTA dense solver
+constexpr int kMaxN = 512;      // unknowns of one core (r*p*r): every shape the assembly supports (ranks <= 8, p <= 8); cores whose
+                                // system does not fit the solver's shared memory (n > ~140) are solved in a global-memory workspace
 
 enum BasisKind : int { BASIS_PHI = 0, BASIS_POLY = 1, BASIS_LEGENDRE = 2 };
 

@@ -1346,11 +1346,16 @@ k_micro_solve(MicroSolveArgs a) {
     long long t_phase = a.clk ? clock64() : 0;
     const int n = a.rl * a.p * a.rr;
     const int ld = n + 3;
+    // Cores whose system does not fit the shared memory of the CTA (n > ~140 unknowns) keep the matrix region and the
+    // staged moments in the global workspace a.big_ws (L2-resident, a few MB): the same code on generic pointers — slower
+    // per entry, but every core shape the assembly kernels accept can be solved.  The small vectors stay in shared memory.
+    double* const front = a.big_ws ? a.big_ws : sm;
+    double* const tail = a.big_ws ? sm : sm + dense_front_doubles(n);
     SolveScratch S;
-    S.A = sm;                                   // (n+2) x (n+3): augmented normal equations / Jacobi G / QR work matrix
-    S.G = sm;
-    S.V = sm + (size_t)(n + 2) * (n + 3);       // n^2     : Jacobi vectors (n <= kJacobiMaxN only)
-    S.x = sm + dense_front_doubles(n);          // n
+    S.A = front;                                // (n+2) x (n+3): augmented normal equations / Jacobi G / QR work matrix
+    S.G = front;
+    S.V = front + (size_t)(n + 2) * (n + 3);    // n^2     : Jacobi vectors (n <= kJacobiMaxN only)
+    S.x = tail;                                 // n
     S.sc = S.x + n;                             // n
     S.bvec = S.sc + n;                          // n
     S.red = S.bvec + n;                         // n       : Jacobi solution scratch
@@ -1358,7 +1363,8 @@ k_micro_solve(MicroSolveArgs a) {
     double* qrR = W + kMaxR * kMaxP * kMaxR;    // kMaxR^2
     double* tau = qrR + kMaxR * kMaxR;          // kMaxR
     double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
-    double* stage_buf = vbuf + kMaxR * kMaxP + 16;   // a.n_slots : the assembly kernel's summed slots
+    double* stage_buf = a.big_ws ? a.big_ws + dense_front_doubles(n)      // a.n_slots : the assembly kernel's summed slots
+                                 : vbuf + kMaxR * kMaxP + 16;
     __shared__ int s_path, s_rank, s_ok, s_sym, s_sweeps;
     __shared__ double s_red[4], s_wmax[32], s_wdif[32];
 
@@ -1426,8 +1432,11 @@ k_micro_solve(MicroSolveArgs a) {
                 // ordering with one column per lane group resident in registers (one pass, one barrier per round);
                 // beyond: 32 lanes per pair and the round-robin tournament in two passes per round
                 // (bench/micro/vh_solve.cu times both on cores of 65..128 unknowns)
-                if (n <= 128) rank = vh_lstsq<kDenseThreads, 16, 4>(Amat, n, S.bvec, xtmp, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
-                else rank = vh_lstsq<kDenseThreads, 32, 3>(Amat, n, S.bvec, xtmp, vh_carve(sm, n), a.clk ? &s_sweeps : nullptr);
+                // (UMAX = 16-byte row chunks per lane: 2 * 32 * UMAX rows)
+                if (n <= 128) rank = vh_lstsq<kDenseThreads, 16, 4>(Amat, n, S.bvec, xtmp, vh_carve(front, n), a.clk ? &s_sweeps : nullptr);
+                else if (n <= 192) rank = vh_lstsq<kDenseThreads, 32, 3>(Amat, n, S.bvec, xtmp, vh_carve(front, n), a.clk ? &s_sweeps : nullptr);
+                else if (n <= 256) rank = vh_lstsq<kDenseThreads, 32, 4>(Amat, n, S.bvec, xtmp, vh_carve(front, n), a.clk ? &s_sweeps : nullptr);
+                else rank = vh_lstsq<kDenseThreads, 32, 8>(Amat, n, S.bvec, xtmp, vh_carve(front, n), a.clk ? &s_sweeps : nullptr);
                 if (rank >= 0 && a.clk && threadIdx.x == 0) atomicAdd((unsigned long long*)(a.clk + 7), (unsigned long long)s_sweeps);
             }
             if (rank < 0) {
@@ -1565,15 +1574,27 @@ static int set_smem_attributes() {
 
 #define BSDE_TRY_RC(expr) do { const int _rc = (expr); if (_rc) return _rc; } while (0)
 
+constexpr size_t kDenseSmemLimit = 220 * 1024;
+// doubles of k_micro_solve's shared memory besides the matrix region and the staged moments (keep in sync with its layout)
+static size_t dense_tail_doubles_n(int n) {
+    return 4 * (size_t)n + kMaxR * kMaxP * kMaxR + kMaxR * kMaxR + kMaxR + kMaxR * kMaxP + 16 + 16;
+}
+
+size_t micro_solve_workspace_bytes(int n, int n_slots) {
+    const size_t slots = (size_t)(n_slots > 0 ? n_slots : 0);
+    const size_t all = (dense_front_doubles(n) + dense_tail_doubles_n(n) + slots) * sizeof(double);
+    if (all <= kDenseSmemLimit) return 0;
+    return (dense_front_doubles(n) + slots + 16) * sizeof(double);
+}
+
 int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_launches) {
     const int n = a.rl * a.p * a.rr;
     if (n > kMaxN) return fail_msg(2, "micro_solve: n = %d unknowns exceeds the in-CTA solver limit %d", n, kMaxN);
     if (a.direction > 0 && a.rl * a.p < a.rr) return fail_msg(2, "micro_solve: left QR needs r_j*p >= r_{j+1} (%d*%d < %d)", a.rl, a.p, a.rr);
     if (a.direction < 0 && a.p * a.rr < a.rl) return fail_msg(2, "micro_solve: right QR needs p*r_{j+1} >= r_j (%d*%d < %d)", a.p, a.rr, a.rl);
     // keep in sync with the layout at the top of k_micro_solve
-    const size_t doubles = dense_front_doubles(n) + 4 * (size_t)n + kMaxR * kMaxP * kMaxR + kMaxR * kMaxR + kMaxR +
-                           kMaxR * kMaxP + 16 + (size_t)(a.n_slots > 0 ? a.n_slots : 0) + 16;
-    const size_t bytes = doubles * sizeof(double);
+    const size_t doubles = dense_front_doubles(n) + dense_tail_doubles_n(n) + (size_t)(a.n_slots > 0 ? a.n_slots : 0);
+    size_t bytes = doubles * sizeof(double);
     BSDE_TRY_RC(set_smem_attributes());
     // plain micro-step of at most 64 unknowns (ALS and SALSA): the register-resident kernel, which also holds the
     // truncated path; everything else (larger cores, LU, explicit systems, the parity dump) goes to k_micro_solve
@@ -1586,7 +1607,12 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_laun
         k_micro_solve_fast<<<1, kFastThreads, fd * sizeof(double), st>>>(a);
         BSDE_CUDA_OK(cudaGetLastError());
     } else {
-        if (bytes > 220 * 1024) return fail_msg(2, "micro_solve: n = %d needs %zu B of shared memory", n, bytes);
+        if (bytes > kDenseSmemLimit) {      // matrix region and staged moments in the global workspace
+            if (!a.big_ws) return fail_msg(2, "micro_solve: n = %d needs %zu B of shared memory and no workspace was provided", n, bytes);
+            bytes = dense_tail_doubles_n(n) * sizeof(double);
+        } else if (a.big_ws) {
+            return fail_msg(2, "micro_solve: workspace given for a core of %d unknowns that fits shared memory", n);
+        }
         k_micro_solve<<<1, kDenseThreads, bytes, st>>>(a);
         BSDE_CUDA_OK(cudaGetLastError());
     }

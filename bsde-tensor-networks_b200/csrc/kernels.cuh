@@ -114,7 +114,11 @@ struct MicroSolveArgs {
     int* hint = nullptr;                // device int of this core: != 0 = its last solve truncated (k_micro_solve_fast goes straight to vh_lstsq)
     const double* A_direct = nullptr;   // explicit n x n system (then rl = n, p = rr = 1 and moments is unused)
     const double* b_direct = nullptr;
+    double* big_ws = nullptr;           // device workspace of micro_solve_workspace_bytes() for cores beyond the shared-memory solver
 };
+// Bytes of global-memory workspace k_micro_solve needs for a core of n unknowns whose moments fill n_slots slots
+// (0: the system fits the shared memory of the one CTA).  The caller provides it as MicroSolveArgs::big_ws.
+size_t micro_solve_workspace_bytes(int n, int n_slots);
 // *extra_launches: kernels launched in front of k_micro_solve (the fast kernel, see dense.cu)
 int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_launches = nullptr);
 // pvec_dev: optional per-core basis sizes (device, d ints) for trains with a ragged `shape` (tensor_train.py:18-32)

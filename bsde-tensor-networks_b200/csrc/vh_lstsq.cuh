@@ -130,8 +130,10 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
     // nwarps keys, so the dependent chain between two steps is: barrier, one shared-memory load, log2(nwarps) shuffles.
     constexpr int KIT = (2 * LP * UMAX + TPR - 1) / TPR;       // column-update iterations per lane (rows capacity / TPR)
     static_assert(nwarps <= 32, "one key per warp");
-    auto make_key = [](double v, int i) -> long long {
-        return v > 0.0 ? ((__double_as_longlong(v) & ~0xffll) | (long long)(255 - i)) : LLONG_MIN;
+    // (systems of more than 256 rows: 10 index bits, ties within 2^-42)
+    const long long kmask = n <= 256 ? 0xffll : 0x3ffll;
+    auto make_key = [kmask](double v, int i) -> long long {
+        return v > 0.0 ? ((__double_as_longlong(v) & ~kmask) | (kmask - (long long)i)) : LLONG_MIN;
     };
     int r = 0;
 #ifndef VH_FORCE_LEFT_LOOKING
@@ -256,7 +258,7 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
         }
         key = __shfl_sync(full, key, 0);
         if (key == LLONG_MIN) break;                   // nothing positive left (uniform over the CTA)
-        const int jk = 255 - (int)(key & 0xff);
+        const int jk = (int)(kmask - (key & kmask));
         const double bv = d[jk];
         if (!(bv > tolpiv)) break;
         VH_T(9);
@@ -467,12 +469,15 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
         __syncthreads();
     } else if (r > 1) {
         // the tournament's pairs, once per solve: tab[step * NP + k] = p | q << 8 (q = 255: padding of an odd r)
+        // (more than 254 columns do not fit the 8-bit fields: the pairs are then computed on the fly)
         unsigned short* tab = S.tab;
-        for (int e = tid; e < (m - 1) * NP; e += T) {
-            int p, q;
-            vh_rr_pair(e % NP, e / NP, m, p, q);
-            tab[e] = (unsigned short)(p | ((q < r ? q : 255) << 8));
-        }
+        const bool use_tab = r <= 254;
+        if (use_tab)
+            for (int e = tid; e < (m - 1) * NP; e += T) {
+                int p, q;
+                vh_rr_pair(e % NP, e / NP, m, p, q);
+                tab[e] = (unsigned short)(p | ((q < r ? q : 255) << 8));
+            }
         if (tid == 0) { S.flags[0] = 0; S.flags[1] = 0; }
         __syncthreads();
         for (; sweep < 30; sweep++) {
@@ -481,8 +486,11 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
                 for (int k0 = 0; k0 < NP; k0 += PG) {
                     const int k = k0 + pg;
                     int p = 0, q = 255;
-                    if (k < NP) { const unsigned pq = tab[step * NP + k]; p = pq & 255; q = pq >> 8; }
-                    const bool valid = q != 255;
+                    bool valid = false;
+                    if (k < NP) {
+                        if (use_tab) { const unsigned pq = tab[step * NP + k]; p = pq & 255; q = pq >> 8; valid = q != 255; }
+                        else { vh_rr_pair(k, step, m, p, q); valid = q < r; }
+                    }
                     VH_T(1);
                     double2 xp[UMAX], xq[UMAX];
                     double2* cp = reinterpret_cast<double2*>(G + (size_t)p * ldg);
