@@ -1208,13 +1208,17 @@ int bsde_paths_simulate(bsde_ctx* c, int model_id, const double* params, int d, 
     Guard g(c);
     double r, sigma0;
     BSDE_TRY(model_params(model_id, params, r, sigma0));
-    if (d < 1 || N < 1 || steps < 1 || !x0_host || !x_out_dev) return fail_msg(2, "paths_simulate: bad arguments");
+    if (d < 1 || N < 1 || steps < 1 || !x_out_dev) return fail_msg(2, "paths_simulate: bad arguments");
     if (replay && !xi_dev) return fail_msg(2, "paths_simulate: replay needs xi_dev");
-    BSDE_TRY(c->tmp.ensure(sizeof(double) * d));
-    BSDE_CUDA_OK(cudaMemcpyAsync(c->tmp.p, x0_host, sizeof(double) * d, cudaMemcpyHostToDevice, c->stream));
-    BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    const double* x0_dev = nullptr;          // x0_host == NULL: the caller filled x_out_dev[0][d][N] with per-sample starting points
+    if (x0_host) {
+        BSDE_TRY(c->tmp.ensure(sizeof(double) * d));
+        BSDE_CUDA_OK(cudaMemcpyAsync(c->tmp.p, x0_host, sizeof(double) * d, cudaMemcpyHostToDevice, c->stream));
+        BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+        x0_dev = c->tmp.as<double>();
+    }
     const double dt = T / steps;
-    BSDE_TRY(launch_paths(model_id, sigma0, sqrt(dt), d, N, steps, c->tmp.as<double>(), seed, sample_offset, replay, xi_dev,
+    BSDE_TRY(launch_paths(model_id, sigma0, sqrt(dt), d, N, steps, x0_dev, seed, sample_offset, replay, xi_dev,
                           x_out_dev, c->stream));
     c->launches++;
     return 0;

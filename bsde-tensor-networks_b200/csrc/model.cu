@@ -59,7 +59,7 @@ struct PathArgs {
     double sqrt_dt;
     int d, steps;
     int64_t N;
-    const double* x0;    // [d] device
+    const double* x0;    // [d] device: one starting point for every sample; null: slab 0 of x holds per-sample starting points
     uint64_t seed;
     int64_t sample_offset;
     int replay;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) k_paths(PathArgs a) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int j = (int)(t / a.N);
         const int64_t s = t - (int64_t)j * a.N;
-        double x = a.x0[j];
+        double x = a.x0 ? a.x0[j] : a.x[t];
         a.x[t] = x;
         if (!a.replay && a.xi) a.xi[t] = 0.0;     // xi[:,0] is never used (path.py:34)
         double nrm0 = 0.0, nrm1 = 0.0;

@@ -226,10 +226,17 @@ class Backend:
 
     # ---- paths, targets ----------------------------------------------------------------------------------
     def paths_simulate(self, model_id, params, x0, N, steps, T, seed=0, sample_offset=0, xi=None, keep_xi=True):
-        """x [steps+1][d][N] (and xi in the same layout).  `xi` given => replay of host-supplied increments."""
+        """x [steps+1][d][N] (and xi in the same layout).  `xi` given => replay of host-supplied increments.
+        x0: (d,) one starting point for all samples, or (N, d) one per sample (path.py:6)."""
         x0 = _f64(x0)
-        d = x0.shape[0]
+        per_sample = x0.ndim == 2
+        if per_sample and x0.shape[0] != N:
+            raise ValueError(f"X0 has {x0.shape[0]} rows for {N} samples")
+        d = x0.shape[-1]
         x = self.empty(steps + 1, d, N)
+        if per_sample:
+            x[0].copy_(self.to_device(np.ascontiguousarray(x0.T)))
+            x0 = None
         replay = xi is not None
         if replay:
             xi = self.to_device(xi)

@@ -27,10 +27,11 @@ def simulate_paths(model, X0, n_steps, batch_size, paths="philox", seed=0, sampl
     from bsde_solver._backend import get_backend
 
     be = get_backend()
-    x0 = xp.asarray(X0, dtype=xp.float64)
-    x0 = x0[0] if x0.ndim == 2 else x0
+    from bsde_solver.stochastic.path import _x0_row
+
+    x0, _ = _x0_row(X0)                       # one row when all samples start from the same point, else (batch, d)
     if paths == "numpy":
-        xi_host = xp.random.randn(batch_size, n_steps + 1, x0.shape[0])                    # path.py:26
+        xi_host = xp.random.randn(batch_size, n_steps + 1, x0.shape[-1])                   # path.py:26
         xi = be.to_device(xp.ascontiguousarray(xi_host.transpose(1, 2, 0)))
         return be.paths_simulate(model.model_id, model.params(), x0, batch_size, n_steps, model.T, xi=xi)
     if paths == "philox":

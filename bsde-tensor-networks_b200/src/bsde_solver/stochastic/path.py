@@ -10,11 +10,13 @@ from bsde_solver.bsde import BackwardSDE
 
 
 def _x0_row(X0):
+    """(d,) -> itself; (batch, d) with identical rows (every reference script tiles one X0) -> that row, d doubles to
+    ship; a general (batch, d) X0 -> itself, shipped sample by sample."""
     X0 = xp.asarray(X0, dtype=xp.float64)
     if X0.ndim == 1:
         return X0, None
     if not (X0 == X0[0]).all():
-        raise ValueError("the CUDA path kernel starts every sample from the same X0 (as all reference scripts do)")
+        return xp.ascontiguousarray(X0), X0.shape[0]
     return xp.ascontiguousarray(X0[0]), X0.shape[0]
 
 

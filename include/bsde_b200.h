@@ -146,7 +146,9 @@ BSDE_API int bsde_tt_hessian(bsde_ctx* ctx, int basis_kind, int d, int p, int64_
  *      src/scripts/pipeline.py:129-133, src/scripts/pipeline_explicit.py:97-102) ---------------------------- */
 /* x_out_dev [steps+1][d][N]; xi_dev [steps+1][d][N] is read when replay != 0 (host-supplied increments),
  * otherwise increments come from Philox4x32-10 keyed by (seed; sample_offset + sample, step, asset) and are
- * written to xi_dev when it is non-NULL. */
+ * written to xi_dev when it is non-NULL.  x0_host [d] is the common starting point of all samples (every reference script
+ * tiles one X0); x0_host == NULL: the caller has filled slab 0 of x_out_dev ([d][N]) with one starting point per sample
+ * (path.py:6 takes a general (N, d) X0). */
 BSDE_API int bsde_paths_simulate(bsde_ctx* ctx, int model_id, const double* params, int d, int64_t N, int steps, double T,
                         const double* x0_host, uint64_t seed, int64_t sample_offset, int replay, double* xi_dev,
                         double* x_out_dev);

@@ -248,6 +248,32 @@ def test_paths_replay_is_bit_exact(backend, golden):
         np.testing.assert_array_equal(x.permute(2, 0, 1).cpu().numpy(), x_ref)
 
 
+def test_paths_from_per_sample_starting_points(backend):
+    """generate_trajectories takes a general (batch, dim) X0 (path.py:6-34; every reference script tiles one row): the
+    replay of host increments from per-sample starting points against the oracle's Euler scheme, bit for bit, through
+    the reference-shaped entry point and the device-resident one."""
+    import oracle.tt_oracle as O
+    from bsde_solver.bsde import HJB, BlackScholes
+    from bsde_solver.stochastic.path import generate_trajectories, generate_trajectories_device
+
+    rng = np.random.RandomState(21)
+    N, d, steps = 777, 5, 6
+    X0 = 0.5 + rng.rand(N, d)
+    for model, omodel in ((BlackScholes(X0, 1.0 / steps, 1.0, 0.05, 0.4), O.BlackScholes(1.0, 0.05, 0.4)),
+                          (HJB(X0, 1.0 / steps, 1.0, np.sqrt(2)), O.HJB(1.0, np.sqrt(2)))):
+        np.random.seed(4)
+        x, xi = generate_trajectories(X0, steps, model)
+        assert x.shape == (N, steps + 1, d)
+        x_ref, _ = O.generate_trajectories(X0, steps, omodel, xi=xi)
+        np.testing.assert_array_equal(x, x_ref)
+        np.testing.assert_array_equal(x[:, 0], X0)
+        xd, _ = generate_trajectories_device(X0, steps, model, seed=9)
+        np.testing.assert_array_equal(xd[0].cpu().numpy(), X0.T)
+        assert np.isfinite(xd.cpu().numpy()).all() and not np.array_equal(xd[1].cpu().numpy(), X0.T)
+    with pytest.raises(ValueError):
+        backend.paths_simulate(1, np.array([1.0]), X0, N + 1, steps, 1.0)
+
+
 def test_model_h_g_match_reference(backend, golden):
     from bsde_solver.bsde import HJB, BlackScholes
 
