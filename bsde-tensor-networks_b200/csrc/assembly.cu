@@ -509,15 +509,18 @@ k_assemble_rb(AsmArgs a) {
 //   tile lambda = 0..9 :  row g = rho = 0..7                     A = RR_g(s) L_a(s),  B = B_g(s) L_a'(s)
 //   tile 10, 11        :  row g = lambda = 0..7, rho = 8 | 9      A = LL_g(s) * RR_8|9(s)
 //   tile 12            :  row g < 4: lambda = 8 + g/2, rho = 8 + g%2
-//   tile 13, 14 (M2)   :  row g: a = 2 (tile - 13) + g/4, b = g%4  A = L_a(s) * R_b(s),  B = (phi_m y)(s)
+//   tile 13 (M2)       :  row g: a = g/2, m_hi = g%2;  column c: b = c/2, m_lo = c%2;  m = 2 m_hi + m_lo
+//                          A = (L_a x^(2 m_hi))(s),  B = (R_b x^(m_lo) y)(s)       — the 4 x 4 x 4 entries of V^T y fill
+//                          exactly one tile (until round 2: two half-empty tiles, rows (a, b) x columns m, with the
+//                          A fragments multiplied out per k-step: 15 DMMA + 13 DMUL per k-step instead of 14 + 11)
 //
-// (g = lane / 4 = row of the fragment, s = the lane's sample of the k-step).  RR_g, LL_g, R_b and the two B fragments
+// (g = lane / 4 = row of the fragment, s = the lane's sample of the k-step).  RR_g, LL_g, the M2 fragments and B_g
 // are one fragment load per k-step each; RR_8, RR_9 and L_0..3 depend on the sample only, are staged sample-major and
 // read with 3 LDS.128 per k-step (a 16-byte load costs 4 wavefronts however few distinct addresses it has, which is why
 // LL_lambda(s) = L_a(s) L_a'(s) is formed in registers as (RR_g L_a) L_a' rather than broadcast from shared memory).
-// 8 shared-memory instructions and 22 wavefronts per k-step of 15 DMMAs instead of 32 and 64.
-constexpr int kR4Tiles = 15;
-constexpr int kR4FmRows = 32;            // function-major rows: RR_0..7 | B_0..6, ZERO | LL_0..7 | R_0..3 | phi_m y
+// 8 shared-memory instructions and 22 wavefronts per k-step of 14 DMMAs instead of 32 and 64.
+constexpr int kR4Tiles = 14;
+constexpr int kR4FmRows = 40;            // function-major rows: RR_0..7 | B_0..6, ZERO | LL_0..7 | L_a x^(2h) (8) | R_b x^l y (8)
 constexpr int kR4SmStride = 10;          // sample-major doubles per sample: RR_8, RR_9, L_0..3, 4 pad (conflict-free 16-byte reads)
 constexpr int kR4WarpDoubles = kR4FmRows * kStride + 32 * kR4SmStride;
 
@@ -614,10 +617,9 @@ k_assemble_r4(AsmArgs a) {
     const int g = lane >> 2;
     // per-lane fragment sources
     const double* fm = ws + (lane & 3);
-    const int o_rr = g * kStride, o_bf = (8 + g) * kStride, o_llg = (16 + g) * kStride, o_rb = (24 + (g & 3)) * kStride;
-    const int o_fy = (g < 4 ? 28 + g : 15) * kStride;
+    const int o_rr = g * kStride, o_bf = (8 + g) * kStride, o_llg = (16 + g) * kStride;
+    const int o_a13 = (24 + g) * kStride, o_b13 = (32 + g) * kStride;
     const double2* smp = reinterpret_cast<const double2*>(wsm + (lane & 3) * kR4SmStride);
-    const bool hi = (g & 4) != 0;        // M2 tiles: a = 2 t + (g >> 2)
     const bool t12 = g < 4, t12l = (g & 2) != 0, t12r = (g & 1) != 0;
 
     double acc[kR4Tiles][2];
@@ -657,15 +659,22 @@ k_assemble_r4(AsmArgs a) {
                 ws[k * kStride + lane] = rr[k];
                 ws[(16 + k) * kStride + lane] = ll[k];
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++) ws[(24 + k) * kStride + lane] = raw.R[k];
             const double x = raw.xb[0];
             double pw = vm;
 #pragma unroll
             for (int k = 0; k < 7; k++) {
                 ws[(8 + k) * kStride + lane] = pw;
-                if (k < 4) ws[(28 + k) * kStride + lane] = pw * yv;
                 pw *= x;
+            }
+            {   // M2 fragments: rows (a, m_hi) = L_a x^(2 m_hi), columns (b, m_lo) = R_b x^(m_lo) y
+                const double x2 = x * x, xy = x * yv;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    ws[(24 + 2 * q) * kStride + lane] = raw.L[q];
+                    ws[(25 + 2 * q) * kStride + lane] = raw.L[q] * x2;
+                    ws[(32 + 2 * q) * kStride + lane] = raw.R[q] * yv;
+                    ws[(33 + 2 * q) * kStride + lane] = raw.R[q] * xy;
+                }
             }
             accyy += yv * yv;
         }
@@ -683,7 +692,7 @@ k_assemble_r4(AsmArgs a) {
         for (int step = 0; step < 8; step++) {
             const double* w = fm + step * 4;
             const double2* sp = smp + step * (4 * kR4SmStride / 2);
-            const double rrg = w[o_rr], bf = w[o_bf], llg = w[o_llg], rb = w[o_rb], fy = w[o_fy];
+            const double rrg = w[o_rr], bf = w[o_bf], llg = w[o_llg], a13 = w[o_a13], b13 = w[o_b13];
             const double2 r89 = sp[0], s01 = sp[1], s23 = sp[2];
             // tile lambda = (a, a'):  A = RR_g L_a,  B = B_g L_a'  — 8 products feed 10 DMMAs (the FP64 pipe is shared by
             // DMMA and DMUL, and a 16-byte broadcast load costs 4 wavefronts however few distinct addresses it has, so
@@ -705,8 +714,7 @@ k_assemble_r4(AsmArgs a) {
             // tile 12: LL_8 = L_2 L_3, LL_9 = L_3 L_3  ->  A = L_2|3 RR_8|9,  B = B_g L_3
             const double c12 = t12 ? (t12l ? s23.y : s23.x) : 0.0;
             dmma884(acc[12][0], acc[12][1], c12 * (t12r ? r89.y : r89.x), v3);
-            dmma884(acc[13][0], acc[13][1], (hi ? s01.y : s01.x) * rb, fy);
-            dmma884(acc[14][0], acc[14][1], (hi ? s23.y : s23.x) * rb, fy);
+            dmma884(acc[13][0], acc[13][1], a13, b13);
         }
         __syncwarp();
     }
@@ -1071,7 +1079,7 @@ int asm_plan_build(AsmPlan& P, int rl, int p, int rr, int mono, int64_t N, int s
         for (int m = 0; m < p; m++)
             for (int a = 0; a < rl; a++)
                 for (int b = 0; b < rr; b++)
-                    P.h_gather[base2 + ((size_t)m * rl + a) * rr + b] = (13 + (a >> 1)) * 64 + ((a & 1) * 4 + b) * 8 + m;
+                    P.h_gather[base2 + ((size_t)m * rl + a) * rr + b] = 13 * 64 + (a * 2 + (m >> 1)) * 8 + (b * 2 + (m & 1));
         P.tab_entries = 0;
         tab_smem = 0;
     } else if (P.rb_class >= 0) {
