@@ -345,7 +345,7 @@ __device__ int vh_lstsq(AFn Aat, int n, const double* __restrict__ bvec, double*
     // large columns, so their angles never settle — on the heavily rank-deficient systems of small sample sets (the
     // reference's benchmark point N = 2000, r = p = 5: numerical rank 26..66 of 125) a handful of such pairs kept the
     // sweeps going up to the limit of 30 (7 with this rule; same ranks, solutions equal to 1e-11 in the fit seminorm:
-    // scratch/sweeps_r5.py).  They are still rotated like every other pair.
+    // bench/micro/jacobi_studies/sweeps_r5.py).  They are still rotated like every other pair.
     const double sub_cut = 0.25 * DBL_EPSILON * (double)n * dmax0;
     const double thr2_sub = 1e-4;
     int sweep = 0;
