@@ -1072,7 +1072,17 @@ k_micro_solve_fast(MicroSolveArgs a) {
     double* vbuf = tau + kMaxR;                 // kMaxR*kMaxP
     double* stage = vbuf + kMaxR * kMaxP + 16;  // a.n_slots
     __shared__ double s_red[8];
+    // Thread (ty, tx) of the 16 x 16 grid.  BSDE_FAST_COLMAJOR (default): tx = tid / 16, so the 16 threads that publish a
+    // pivot column pair (tx == t % 16) are ONE half-warp — the other seven warps never enter the publishing branch and start
+    // their share of the trailing update at once (with tx = tid % 16 every warp held two of them and walked through it).
+#ifndef BSDE_FAST_COLMAJOR
+#define BSDE_FAST_COLMAJOR 1
+#endif
+#if BSDE_FAST_COLMAJOR
+    const int tid = threadIdx.x, ty = tid & 15, tx = tid >> 4;
+#else
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+#endif
 
     // ---- the map entries of this thread's blocks (global loads issued before the moments are staged) ----
     const uint16_t* map = a.expand_map;
