@@ -1106,7 +1106,11 @@ k_micro_solve_fast(MicroSolveArgs a) {
                     if (rowok[ai] && colok[bi] && j < n) {
                         if (Rw[ai] < NP) {
                             const int i = 2 * Rw[ai] + r;
+#if BSDE_FAST_COLMAJOR          // lanes run over the rows: read the mirror entry (the map is symmetric), 2-byte stride across the warp
+                            if (i < n) { if (j <= i) m = map[j * n + i]; }
+#else
                             if (i < n) { if (j <= i) m = map[i * n + j]; }
+#endif
                         } else {
                             m = r == 0 ? (int)map[n * n + j] : -3;
                         }
@@ -1115,7 +1119,9 @@ k_micro_solve_fast(MicroSolveArgs a) {
                     }
                     midx[ai][bi][r][c] = m;
                 }
+    const int hint0 = a.hint ? *a.hint : 0;                    // (read with the other global loads, used after the staging)
     const int dmap = tid < n ? (int)map[tid * n + tid] : -1;
+    const int bmap = tid < n ? (int)map[n * n + tid] : 0;      // (loaded here: a global round trip in front of the factorisation otherwise)
     for (int e = tid; e < a.n_slots; e += kFastThreads) stage[e] = load_moment(a, e);
     __syncthreads();
     // ---- equilibration, trace, positivity of the diagonal ----
@@ -1135,7 +1141,7 @@ k_micro_solve_fast(MicroSolveArgs a) {
         }
     }
     __syncthreads();
-    if (tid < n) bv[tid] = stage[map[n * n + tid]];
+    if (tid < n) bv[tid] = stage[bmap];
     if (tid < 32) {
         double tr = 0.0;
         int bad = 0;
@@ -1177,7 +1183,7 @@ k_micro_solve_fast(MicroSolveArgs a) {
     // a core stay rank-deficient from sweep to sweep once the fit has converged, so the factorisation and its acceptance
     // tests (~35k cycles) are not tried again — vh_lstsq returns lstsq's answer whatever the conditioning, and clears the
     // hint again when it finds the system comfortably regular.  (uniform: one word read by every thread)
-    if (a.hint && *a.hint != 0) accepted = false;
+    if (hint0 != 0) accepted = false;
     BSDE_PHASE(0);
     long long t_sub = t_phase;
     if (a.stop_after == 1) return;
