@@ -142,3 +142,19 @@ def test_sweep_driver_counts_the_algorithmic_flops_of_the_survey():
     assert mod.flops_per_sample_sweep(100, 4, 4) == 866208       # C3
     assert mod.flops_per_sample_sweep(10, 2, 3) == 3396          # C2
     assert mod.flops_per_sample_sweep(500, 4, 4) == 4399008      # C5, d = 500
+
+
+def test_starting_points_of_the_path_simulation():
+    """generate_trajectories(X0, ...) (path.py:6-34): a tiled X0 — what every reference script passes — ships one row, a
+    general (batch, dim) X0 ships every sample's starting point."""
+    from bsde_solver.stochastic.path import _x0_row
+
+    row = np.array([1.0, 0.5, 1.0])
+    x0, n = _x0_row(row)
+    assert x0.shape == (3,) and n is None
+    x0, n = _x0_row(np.tile(row, (7, 1)))
+    assert x0.shape == (3,) and n == 7 and x0.flags["C_CONTIGUOUS"]
+    X0 = np.arange(12.0).reshape(4, 3)
+    x0, n = _x0_row(X0[:, ::1])
+    assert x0.shape == (4, 3) and n == 4
+    np.testing.assert_array_equal(x0, X0)
