@@ -1294,7 +1294,7 @@ int bsde_normal_eq(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const d
 int bsde_solve(bsde_ctx* c, int n, const double* A_host, const double* b_host, int solver_id, double* x_host, int* info_host) {
     BSDE_CHECK_CTX(c);
     Guard g(c);
-    if (n < 1 || n > 100) return fail_msg(2, "solve: n = %d outside 1..100", n);
+    if (n < 1 || n > kMaxN) return fail_msg(2, "solve: n = %d outside 1..%d", n, kMaxN);
     if (solver_id < 0 || solver_id > 3) return fail_msg(2, "Unknown method %d", solver_id);
     if (!A_host || !b_host || !x_host) return fail_msg(2, "solve: null pointer");
     BSDE_TRY(c->dbg.ensure(sizeof(double) * ((size_t)n * n + 2 * n)));
@@ -1309,10 +1309,21 @@ int bsde_solve(bsde_ctx* c, int n, const double* A_host, const double* b_host, i
     a.rl = n; a.p = 1; a.rr = 1; a.direction = 0; a.solver = solver_id;
     a.core_j = x; a.info = info; a.A_direct = A; a.b_direct = b;
     a.force_onesided = (int)c->svd_onesided;
+    if (const size_t ws = micro_solve_workspace_bytes(n, 0)) {      // systems beyond the solver's shared memory
+        BSDE_TRY(c->solve_ws.ensure(ws));
+        a.big_ws = c->solve_ws.as<double>();
+    }
     BSDE_TRY(launch_micro_solve(a, c->stream));
     c->launches++;
     BSDE_CUDA_OK(cudaMemcpyAsync(x_host, x, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     BSDE_CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (solver_id == SOLVER_LSTSQ && n > 100) {
+        // beyond 100 unknowns only the positive semi-definite path exists (the Jacobi fallbacks keep a second n x n matrix
+        // in shared memory): an indefinite or non-symmetric system comes back as NaN from the kernel — say so
+        bool bad = false;
+        for (int i = 0; i < n; i++) bad = bad || std::isnan(x_host[i]);
+        if (bad) return fail_msg(2, "solve: 'lstsq' of a system that is not symmetric positive semi-definite (or not finite) is supported up to 100 unknowns, n = %d", n);
+    }
     if (info_host) {
         BSDE_CUDA_OK(cudaMemcpy(info_host, info, sizeof(int) * 4, cudaMemcpyDeviceToHost));
         if (info_host[3] == INT_MAX) info_host[3] = 0;

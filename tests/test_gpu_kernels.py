@@ -180,6 +180,36 @@ def test_solver_matches_numpy_lstsq(backend):
     assert rel(x, np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-9
 
 
+def test_solver_beyond_the_shared_memory_of_one_cta(backend):
+    """solver(A, b, method) (solve.py:6-19) on systems of up to 512 unknowns: beyond ~140 the matrix lives in the solver's
+    global-memory workspace.  Positive definite and rank-deficient Gram matrices against numpy.linalg.lstsq, the three
+    elimination methods against numpy.linalg.solve; what only the small-system fallbacks serve says so."""
+    from bsde_solver._lib import BackendError
+    from bsde_solver.core.optimisation.solve import solver
+
+    rng = np.random.RandomState(17)
+    for n in (150, 256, 400, 512):
+        M = rng.randn(2 * n + 5, n)
+        A = M.T @ M
+        b = rng.randn(n)
+        ref = np.linalg.solve(A, b)
+        for method in ("lstsq", "lu", "qr", "solve"):
+            assert rel(solver(A, b, method), ref) < 1e-9 * max(1.0, np.linalg.cond(A) / 1e4), (n, method)
+    n = 200                                        # numerical rank n - 5: lstsq's minimum-norm solution
+    M = rng.randn(n - 5, n)
+    A = M.T @ M
+    b = A @ rng.randn(n)
+    x, info = backend.solve(A, b, 0)
+    assert info[1] == 1 and info[3] == n - 5
+    assert rel(x, np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-8
+    G = rng.randn(160, 160)                        # not symmetric: general lstsq, served up to 100 unknowns only
+    with pytest.raises(BackendError):
+        solver(G, rng.randn(160), "lstsq")
+    np.testing.assert_allclose(solver(G, G @ np.ones(160), "lu"), np.ones(160), rtol=1e-8)
+    with pytest.raises(BackendError):
+        backend.solve(np.eye(513), np.ones(513), 0)
+
+
 def test_lstsq_eigen_path_symmetric_and_general_input(backend):
     """'lstsq' beyond the Cholesky gate: symmetric systems (every micro-step) go through the two-sided Jacobi
     eigen-decomposition — also indefinite ones, singular values are |lambda| — and non-symmetric input through the
