@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include <algorithm>
+#include <cstdint>
 
 namespace bsde {
 
@@ -237,21 +238,116 @@ __device__ __forceinline__ void chain_step(double (&v)[RB], const double (&phi)[
     for (int b = 0; b < RB; b++) v[b] = nv[b];
 }
 
+// Samples carried per thread by k_tt_eval (a grid stride apart, so every load stays coalesced): one read of a core entry
+// (same address in every lane: a broadcast out of L1) then feeds that many FMAs.  With one sample per thread the kernel
+// issued one load per FMA and ran at 7 TFLOP/s (1.9 ms for 2^20 samples through 100 rank-4 cores, 13 GFLOP); the chain
+// product is FP64-bound, not HBM-bound: 128 flops per 8 bytes read at r = p = 4.
+template <int RB, int PB>
+struct EvalBlocking { static constexpr int S = RB * PB <= 16 ? 4 : 2; };
+
 template <int RB, int PB>
 __global__ void __launch_bounds__(kThreads)
 k_tt_eval(Inputs in, const double* __restrict__ cores, const int64_t* __restrict__ core_off,
           const int* __restrict__ ranks, double* __restrict__ out) {
+    constexpr int S = EvalBlocking<RB, PB>::S;
     const int64_t N = in.N;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
-        double v[RB];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int p = in.p;
+    for (int64_t s0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s0 < N; s0 += stride * S) {
+        int64_t sidx[S];
 #pragma unroll
-        for (int b = 0; b < RB; b++) v[b] = (b == 0) ? 1.0 : 0.0;
+        for (int u = 0; u < S; u++) { const int64_t s = s0 + u * stride; sidx[u] = s < N ? s : N - 1; }   // clamped duplicates are not stored
+        double v[S][RB];
+#pragma unroll
+        for (int u = 0; u < S; u++)
+#pragma unroll
+            for (int b = 0; b < RB; b++) v[u][b] = (b == 0) ? 1.0 : 0.0;
+        // (points: the next asset's coordinates are loaded one asset ahead — the kernel runs at one CTA of 8 warps per SM,
+        // which does not hide a DRAM round trip per asset)
+        const bool points = in.kind != BASIS_PHI;
+        double xn[S];
+#pragma unroll
+        for (int u = 0; u < S; u++) xn[u] = points ? __ldg(in.data + sidx[u]) : 0.0;
         for (int j = 0; j < in.d; j++) {
-            double phi[PB];
-            basis_values<PB>(in, j, s, 0, phi);
-            chain_step<RB, PB>(v, phi, cores + core_off[j], ranks[j], in.p, ranks[j + 1]);
+            double phi[S][PB];
+            if (points) {
+                double xc[S];
+#pragma unroll
+                for (int u = 0; u < S; u++) xc[u] = xn[u];
+                if (j + 1 < in.d) {
+#pragma unroll
+                    for (int u = 0; u < S; u++) xn[u] = __ldg(in.data + (int64_t)(j + 1) * N + sidx[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < S; u++) basis_from_x<PB>(in, xc[u], 0, phi[u]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < S; u++) basis_values<PB>(in, j, sidx[u], 0, phi[u]);
+            }
+            // v <- v . G_j, the same operation order per sample as chain_step
+            const double* __restrict__ c = cores + core_off[j];
+            const int rl = ranks[j], rr = ranks[j + 1];
+            double nv[S][RB];
+#pragma unroll
+            for (int u = 0; u < S; u++)
+#pragma unroll
+                for (int b = 0; b < RB; b++) nv[u][b] = 0.0;
+            if (RB * PB >= 2 && RB * PB <= 16 && rl == RB && rr == RB && p == PB && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+                // interior core of a train with uniform ranks (uniform over the grid): compile-time shape, the PB x RB
+                // entries of row a fetched with 16-byte loads before their FMAs (ncu on the run-time-shaped form below:
+                // a third of the stall samples waited for one core entry at a time)
+                const double2* __restrict__ c2 = reinterpret_cast<const double2*>(c);
+#pragma unroll
+                for (int a = 0; a < RB; a++) {
+                    double2 cv[PB * RB / 2];
+#pragma unroll
+                    for (int k = 0; k < PB * RB / 2; k++) cv[k] = __ldg(c2 + a * (PB * RB / 2) + k);
+#pragma unroll
+                    for (int m = 0; m < PB; m++) {
+                        double t[S];
+#pragma unroll
+                        for (int u = 0; u < S; u++) t[u] = v[u][a] * phi[u][m];
+#pragma unroll
+                        for (int b = 0; b < RB; b++) {
+                            const int e = m * RB + b;
+                            const double cvb = (e & 1) ? cv[e >> 1].y : cv[e >> 1].x;
+#pragma unroll
+                            for (int u = 0; u < S; u++) nv[u][b] = fma(t[u], cvb, nv[u][b]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+            for (int a = 0; a < RB; a++) {
+                if (a < rl) {
+#pragma unroll
+                    for (int m = 0; m < PB; m++) {
+                        if (m < p) {
+                            double t[S];
+#pragma unroll
+                            for (int u = 0; u < S; u++) t[u] = v[u][a] * phi[u][m];
+#pragma unroll
+                            for (int b = 0; b < RB; b++)
+                                if (b < rr) {
+                                    const double cv = __ldg(c + (a * p + m) * rr + b);
+#pragma unroll
+                                    for (int u = 0; u < S; u++) nv[u][b] = fma(t[u], cv, nv[u][b]);
+                                }
+                        }
+                    }
+                }
+            }
+            }
+#pragma unroll
+            for (int u = 0; u < S; u++)
+#pragma unroll
+                for (int b = 0; b < RB; b++) v[u][b] = nv[u][b];
         }
-        out[s] = v[0];
+#pragma unroll
+        for (int u = 0; u < S; u++) {
+            const int64_t s = s0 + u * stride;
+            if (s < N) out[s] = v[u][0];
+        }
     }
 }
 
@@ -513,10 +609,10 @@ int launch_interface_right(const Inputs& in, int j, const double* core, int r_ou
 int launch_tt_eval(const Inputs& in, const double* cores, const int64_t* core_off, const int* ranks_dev, int max_rank,
                    double* out, cudaStream_t st) {
     if (in.p > kMaxP || max_rank > kMaxR) return fail_msg(2, "tt_eval: p=%d rank=%d exceeds limits", in.p, max_rank);
-    const int g = grid_for(in.N);
-#define CALL(RBV)                                                                                          \
-    if (in.p <= 4) k_tt_eval<RBV, 4><<<g, kThreads, 0, st>>>(in, cores, core_off, ranks_dev, out);         \
-    else k_tt_eval<RBV, 8><<<g, kThreads, 0, st>>>(in, cores, core_off, ranks_dev, out)
+    // every thread carries EvalBlocking::S samples a grid stride apart: the grid covers N / S threads
+#define CALL(RBV)                                                                                                                   \
+    if (in.p <= 4) k_tt_eval<RBV, 4><<<grid_for((in.N + EvalBlocking<RBV, 4>::S - 1) / EvalBlocking<RBV, 4>::S), kThreads, 0, st>>>(in, cores, core_off, ranks_dev, out); \
+    else k_tt_eval<RBV, 8><<<grid_for((in.N + EvalBlocking<RBV, 8>::S - 1) / EvalBlocking<RBV, 8>::S), kThreads, 0, st>>>(in, cores, core_off, ranks_dev, out)
     BSDE_DISPATCH_RB(max_rank, CALL);
 #undef CALL
     BSDE_CUDA_OK(cudaGetLastError());
