@@ -8,6 +8,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -106,6 +107,8 @@ struct bsde_ctx {
     int64_t svd_onesided = 0;     // A/B measurement: one-sided Jacobi SVD for symmetric systems too (MicroSolveArgs::force_onesided)
     int64_t fast_solve = 1;       // option: register-resident fast kernel in front of k_micro_solve (dense.cu)
     int64_t fuse_interface = 1;   // option: ALS forms the trailing interface inside the next assembly kernel (als_sweep)
+    int64_t pdl = 1;              // option: kernels of a captured sweep launched with programmatic dependent launch (common.cuh)
+    int64_t graph_edges = 0, graph_pdl_edges = 0;      // stats: edges of the last captured ALS sweep, programmatic ones among them
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     // per-kernel-class device timing (option "profile"): event pairs recorded around eager launches
@@ -343,6 +346,10 @@ struct MicroCtx {
     int* hints = nullptr;      // one int per core (MicroSolveArgs::hint), zeroed at the start of the fit; ALS only
 };
 
+// Programmatic dependent launch inside a captured sweep (single GPU: the sharded sweeps, whose reduction kernel waits on
+// its peers, keep the plain launches they were validated with).
+static int pdl_allowed(const bsde_ctx* c) { return (c->pdl && c->world == 1) ? 1 : 0; }
+
 // assembly + (all-reduce) + solve/QR of core j; direction as MicroSolveArgs
 struct SalsaReg {            // als.py:143-174, all device pointers
     const double* eta = nullptr;
@@ -552,11 +559,26 @@ int fit_als(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double* 
                 const int64_t before = c->launches;
                 BSDE_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                 c->capturing = true;
+                g_pdl_launch = pdl_allowed(c);
                 const int rc = als_sweep(c, m, fused, 0);
+                g_pdl_launch = 0;
                 c->capturing = false;
                 cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
                 if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (e != cudaSuccess) return fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+                {   // how many of the kernel -> kernel edges of the sweep are programmatic (stats "graph_edges", "graph_pdl_edges")
+                    size_t ne = 0;
+                    c->graph_edges = c->graph_pdl_edges = 0;
+                    if (cudaGraphGetEdges_v2(graph, nullptr, nullptr, nullptr, &ne) == cudaSuccess && ne > 0) {
+                        std::vector<cudaGraphNode_t> from(ne), to(ne);
+                        std::vector<cudaGraphEdgeData> ed(ne);
+                        if (cudaGraphGetEdges_v2(graph, from.data(), to.data(), ed.data(), &ne) == cudaSuccess) {
+                            c->graph_edges = (int64_t)ne;
+                            for (size_t i = 0; i < ne; i++) c->graph_pdl_edges += ed[i].type == cudaGraphDependencyTypeProgrammatic;
+                        }
+                    }
+                    (void)cudaGetLastError();
+                }
                 const int64_t per_sweep = c->launches - before;
                 c->launches = before;
                 e = cudaGraphInstantiate(&exec, graph, 0);
@@ -764,7 +786,9 @@ int fit_salsa(bsde_ctx* c, int basis_kind, int d, int p, int64_t N, const double
             const int64_t before = c->launches;
             BSDE_CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             c->capturing = true;
+            g_pdl_launch = pdl_allowed(c);
             const int rc = sweep(it);
+            g_pdl_launch = 0;
             c->capturing = false;
             cudaError_t e = cudaStreamEndCapture(c->stream, &sgraph);
             if (rc) { drop_graph(); return rc; }
@@ -817,6 +841,7 @@ int bsde_ctx_create(int device, bsde_ctx** out) {
     BSDE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail_msg(4, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     bsde_ctx* c = new bsde_ctx();
+    if (const char* e = getenv("BSDE_B200_PDL")) c->pdl = atoi(e);      // A/B switch of option "pdl" for whole test runs
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     BSDE_CUDA_OK(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
@@ -873,6 +898,7 @@ int bsde_ctx_set_option(bsde_ctx* c, const char* name, int64_t value) {
     }
     if (name && !strcmp(name, "fuse_interface")) { c->fuse_interface = value; return 0; }
     if (name && !strcmp(name, "fast_solve")) { c->fast_solve = value; return 0; }
+    if (name && !strcmp(name, "pdl")) { c->pdl = value; return 0; }
     if (name && !strcmp(name, "solve_stop")) { c->solve_stop = value; return 0; }
     if (name && !strcmp(name, "svd_onesided")) { c->svd_onesided = value; return 0; }
     if (name && !strcmp(name, "gate_tier2")) { c->gate_tier2 = value; return 0; }
@@ -914,6 +940,8 @@ int bsde_ctx_get_stat(bsde_ctx* c, const char* name, double* out) {
         return 0;
     }
     if (!strcmp(name, "sm_count")) { *out = c->sm_count; return 0; }
+    if (!strcmp(name, "graph_edges")) { *out = (double)c->graph_edges; return 0; }
+    if (!strcmp(name, "graph_pdl_edges")) { *out = (double)c->graph_pdl_edges; return 0; }
     if (!strcmp(name, "workspace_bytes")) {
         double t = 0;
         for (const DevBuf* b : {&c->bond, &c->partial, &c->moments, &c->cores, &c->meta, &c->coef, &c->tmp, &c->in_copy, &c->y_copy, &c->scalars, &c->dbg, &c->solve_ws})

@@ -41,6 +41,7 @@
 
 namespace bsde {
 
+int g_pdl_launch = 0;      // see common.cuh: launches of a captured sweep carry the programmatic-serialisation attribute
 int g_asm_r4_full = 1;     // option "r4_full": 0 = never take k_assemble_r4's specialised instantiation (A/B measurement)
 
 namespace {
@@ -396,6 +397,8 @@ template <int RT1, int CT1, int RT2, int RB, int PB, int RT3 = 0, int RT4 = 0, i
 __global__ void __launch_bounds__(kAsmThreads, RT3 > 0 ? BSDE_RB_SECT_MIN_BLOCKS : BSDE_RB_MIN_BLOCKS(RT1 * CT1 + RT2 + RT3 + RT4 * CT4))
 k_assemble_rb(AsmArgs a) {
     extern __shared__ double sm[];
+    pdl_wait();
+    pdl_release();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* ws = sm + (size_t)warp * a.warp_doubles;
     unsigned short* stab = reinterpret_cast<unsigned short*>(sm + (size_t)kAsmWarps * a.warp_doubles);
@@ -605,6 +608,13 @@ __global__ void __launch_bounds__(kR4Threads, kR4MinBlocks)
 k_assemble_r4(AsmArgs a) {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t nchunks = (a.in.N + 31) / 32;
+    const int64_t warps_total = (int64_t)gridDim.x * kR4Warps;
+    RawSample<4, 4> raw;
+    // (fetching the first chunk ahead of the wait — its inputs are older than the preceding solve whenever the interface
+    // update is fused — was measured and gains nothing: 238.9-239.5 against 238.8 ms per C3 fit)
+    pdl_wait();
+    pdl_release();
     double* ws = sm + (size_t)warp * a.warp_doubles;
     double* wsm = ws + kR4FmRows * kStride;
     const double* score = sm + a.core_off;
@@ -627,9 +637,6 @@ k_assemble_r4(AsmArgs a) {
     for (int t = 0; t < kR4Tiles; t++) acc[t][0] = acc[t][1] = 0.0;
     double accyy = 0.0;
 
-    const int64_t nchunks = (a.in.N + 31) / 32;
-    const int64_t warps_total = (int64_t)gridDim.x * kR4Warps;
-    RawSample<4, 4> raw;
 #ifndef BSDE_R4_NOPREFETCH
     r4_load_raw<FULL>(a, lane, (int64_t)blockIdx.x * kR4Warps + warp, nchunks, raw);
 #endif
@@ -752,6 +759,8 @@ template <int NJ, int RB, int PB>
 __global__ void __launch_bounds__(kAsmThreads, (NJ >= 16 ? 4 : 6))
 k_assemble(AsmArgs a) {
     extern __shared__ double sm[];
+    pdl_wait();
+    pdl_release();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* ws = sm + (size_t)warp * a.warp_doubles;
     const int group = blockIdx.y;
@@ -799,11 +808,16 @@ k_assemble(AsmArgs a) {
 // slot = y.y).  Coalesced: one block = 32 consecutive slots x 32 row lanes; warp w adds rows w, w+32, ... in order
 // (14 independent loads in flight at 444 rows), then the warp sums are added in warp order — a fixed summation tree of
 // the launch shape, hence bitwise reproducible.  The solve kernel reads the sums through AsmPlan::d_expand.
-constexpr int kRedWarps = 32;
+#ifndef BSDE_RED_WARPS
+#define BSDE_RED_WARPS 16      // measured on the C3 fit (3 row groups): 8 warps 244.7, 16 warps 237.3, 32 warps 239.1 ms per fit
+#endif
+constexpr int kRedWarps = BSDE_RED_WARPS;
 __global__ void __launch_bounds__(32 * kRedWarps)
 k_moment_reduce(const double* __restrict__ partial, int rows, int64_t stride, int n_slots, double* __restrict__ sums,
                 PeerExchange px) {
     __shared__ double part[kRedWarps][33];
+    pdl_wait();
+    pdl_release();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int e = blockIdx.x * 32 + lane;
     // gridDim.y row groups (kRedGroups on a single GPU): group g sums its contiguous share of the partial rows into row g of
@@ -891,6 +905,10 @@ int run_kernel(K kernel, int op, const AsmPlan& plan, const AsmArgs* args, cudaS
         return 0;
     }
     dim3 grid(plan.grid_x, plan.n_groups);
+    if (g_pdl_launch) {
+        BSDE_CUDA_OK(launch_chain(kernel, grid, dim3(plan.warps * 32), plan.smem_bytes, st, true, *args));
+        return 0;
+    }
     kernel<<<grid, plan.warps * 32, plan.smem_bytes, st>>>(*args);
     BSDE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1258,6 +1276,11 @@ int launch_assembly(const AsmPlan& P, const Inputs& in, int j, const double* L, 
         ex = *px;
     }
     if (moment_groups < 1 || moment_groups > kRedGroups) return fail_msg(2, "assembly: %d moment groups", moment_groups);
+    if (g_pdl_launch) {
+        BSDE_CUDA_OK(launch_chain(k_moment_reduce, dim3(red_blocks, moment_groups), dim3(32 * kRedWarps), 0, st, true, partial,
+                                  P.grid_x, P.partial_stride, (int)P.partial_stride, moments, ex));
+        return 0;
+    }
     k_moment_reduce<<<dim3(red_blocks, moment_groups), 32 * kRedWarps, 0, st>>>(partial, P.grid_x, P.partial_stride,
                                                                                (int)P.partial_stride, moments, ex);
     BSDE_CUDA_OK(cudaGetLastError());

@@ -31,6 +31,33 @@ struct Inputs {
     const double* coef;     // BASIS_LEGENDRE: [3][p][p] descending-power polyval coefficients (deriv order, i, k)
 };
 
+// ---- programmatic dependent launch (the three kernels of a micro-step inside a captured sweep) -------------
+// A kernel launched with the programmatic-serialisation attribute becomes resident while its predecessor in the stream
+// still runs and blocks in pdl_wait() until that predecessor has completed and its writes are visible; without the
+// attribute both instructions do nothing.  Every kernel of the chain waits before it releases its own dependant, so
+// at most two consecutive kernels are resident and completion stays transitive along the chain.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl_launch;      // set by api.cu around the launches of a captured sweep (option "pdl")
+
+// kernel<<<grid, block, smem, st>>>(args...), with the programmatic-serialisation attribute when `pdl` is set
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- error-free transformations -----------------------------------------------------------------
 __device__ __forceinline__ void two_prod(double a, double b, double& p, double& e) {
     p = __dmul_rn(a, b);

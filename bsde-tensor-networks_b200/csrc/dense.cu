@@ -1122,7 +1122,30 @@ k_micro_solve_fast(MicroSolveArgs a) {
     const int hint0 = a.hint ? *a.hint : 0;                    // (read with the other global loads, used after the staging)
     const int dmap = tid < n ? (int)map[tid * n + tid] : -1;
     const int bmap = tid < n ? (int)map[n * n + tid] : 0;      // (loaded here: a global round trip in front of the factorisation otherwise)
-    for (int e = tid; e < a.n_slots; e += kFastThreads) stage[e] = load_moment(a, e);
+    // Everything read so far is older than the previous micro-step (the plan's expansion map never changes, the hint word was
+    // written by this core's previous solve): under programmatic dependent launch those loads overlap the reduction.
+    pdl_wait();
+    pdl_release();
+    // (four slots per thread and trip, every load issued before the first addition: the 897 slots of the C3 shape are one
+    // round trip to L2 instead of the three of the compiler's unroll-by-two; same additions in the same order)
+    for (int e0 = tid; e0 < a.n_slots; e0 += 4 * kFastThreads) {
+        double t[4][kRedGroups];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * kFastThreads;
+#pragma unroll
+            for (int g = 0; g < kRedGroups; g++)
+                t[u][g] = (e < a.n_slots && g < a.moment_rows) ? a.moments[(size_t)g * a.n_slots + e] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u * kFastThreads;
+            double acc = t[u][0];
+#pragma unroll
+            for (int g = 1; g < kRedGroups; g++) acc += t[u][g];
+            if (e < a.n_slots) stage[e] = acc;
+        }
+    }
     __syncthreads();
     // ---- equilibration, trace, positivity of the diagonal ----
     if (tid < np) dg[tid] = tid < n ? regularised_diagonal(a, tid, stage[dmap]) : 0.0;
@@ -1359,6 +1382,8 @@ __host__ __device__ inline size_t dense_front_doubles(int n) {
 __global__ void __launch_bounds__(kDenseThreads)
 k_micro_solve(MicroSolveArgs a) {
     extern __shared__ double sm[];
+    pdl_wait();
+    pdl_release();
     long long t_phase = a.clk ? clock64() : 0;
     const int n = a.rl * a.p * a.rr;
     const int ld = n + 3;
@@ -1620,7 +1645,8 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_laun
         const size_t fd = fast_front_doubles(n) + 3 * (size_t)np + kMaxR * kMaxP * kMaxR + kMaxR * kMaxR + kMaxR +
                           kMaxR * kMaxP + 16 + (size_t)a.n_slots + 16;
         if (fd * sizeof(double) > 100 * 1024) return fail_msg(2, "micro_solve: %zu B of shared memory for the fast kernel", fd * sizeof(double));
-        k_micro_solve_fast<<<1, kFastThreads, fd * sizeof(double), st>>>(a);
+        if (g_pdl_launch) BSDE_CUDA_OK(launch_chain(k_micro_solve_fast, dim3(1), dim3(kFastThreads), fd * sizeof(double), st, true, a));
+        else k_micro_solve_fast<<<1, kFastThreads, fd * sizeof(double), st>>>(a);
         BSDE_CUDA_OK(cudaGetLastError());
     } else {
         if (bytes > kDenseSmemLimit) {      // matrix region and staged moments in the global workspace
@@ -1629,7 +1655,8 @@ int launch_micro_solve(const MicroSolveArgs& a, cudaStream_t st, int* extra_laun
         } else if (a.big_ws) {
             return fail_msg(2, "micro_solve: workspace given for a core of %d unknowns that fits shared memory", n);
         }
-        k_micro_solve<<<1, kDenseThreads, bytes, st>>>(a);
+        if (g_pdl_launch) BSDE_CUDA_OK(launch_chain(k_micro_solve, dim3(1), dim3(kDenseThreads), bytes, st, true, a));
+        else k_micro_solve<<<1, kDenseThreads, bytes, st>>>(a);
         BSDE_CUDA_OK(cudaGetLastError());
     }
     if (extra_launches) *extra_launches = 0;
