@@ -428,6 +428,8 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = be.launch_count() - l0
+    sweep_graph = {"edges": int(be.get_stat("graph_edges")), "programmatic_edges": int(be.get_stat("graph_pdl_edges")),
+                   "note": "kernel -> kernel edges of the captured ALS sweep; programmatic = dependent launch (DESIGN.md section 4a)"}
     value = world * N * N_SWEEPS * args.steps / (ms * 1e-3)
     fit_quality = float(torch.linalg.vector_norm(be.tt_eval(inp, ranks, cores) - y) / torch.linalg.vector_norm(y))
 
@@ -490,6 +492,12 @@ def main():
                 "class_us_per_launch": {k: (1e3 * v[0] / v[1] if v[1] else None) for k, v in stats.items()},
                 "solve_kernel_phase_cycles_per_launch": dict(zip(("expand_moments", "solve", "qr", "push_factor", "solve:load", "solve:factor", "solve:back_substitution"),
                                                                  [c / max(1, stats["solve"][1]) for c in solve_phase_cycles]))}
+    # what the kernel EXECUTES on the tensor pipe (interior launches: 14 DMMA.8x8x4 tiles of 512 flops per 4 samples), next to
+    # the algorithmic count above; the two edge launches of a sweep do less, so this overstates the sweep average by < 1 %
+    exec_tflops = N * 1792.0 / (asm_ms / asm_n * 1e-3) / 1e12
+    roofline["executed"] = {"tensor_flops_per_sample": 1792, "tflops": exec_tflops, "frac": exec_tflops / FP64_PEAK_TFLOPS,
+                            "note": "DMMA flops issued per second / FP64 peak; the same pipe also carries 11 DMUL per 4 samples and ~128 "
+                                    "FP64 operations per sample of staging (ncu: DMMA 61 % + FP64 15 % of the pipe busy, profiles/kernels_r02_s3.txt)"}
     try:
         with open(os.path.join(ROOT, "profiles", "assembly_traffic.json")) as f:
             roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
@@ -529,7 +537,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world) if N == N_PER_GPU else dict(workload_config(world), samples_per_gpu=N, workload="reduced-N debugging run (not the benchmark)"),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-            "fit_relative_residual": fit_quality, "solves_per_fit": solve_paths,
+            "fit_relative_residual": fit_quality, "solves_per_fit": solve_paths, "sweep_graph": sweep_graph,
             "converging": converging, "full_solve": full_solve, "e2e_phis": e2e_phis, "multi_gpu_check": mg_check,
             "allreduce": (None if world == 1 else ("fused into the reduction kernel over NVLink peer memory" if getattr(be, "p2p", False) else "ncclAllReduce")),
         }))

@@ -175,6 +175,53 @@ def test_fused_interface_update_is_bit_identical(backend):
         assert out[(1, 1)][1] < out[(0, 1)][1]
 
 
+def test_programmatic_dependent_launch_is_bit_identical(backend):
+    """Option "pdl" (DESIGN.md section 4a): inside the captured sweeps every kernel -> kernel edge becomes programmatic and the
+    solve kernel reads its expansion map ahead of griddepcontrol.wait.  Nothing a kernel consumes may change: same cores to
+    the last bit as with plain launches and as with eager launches, for fast-path shapes, general shapes (k_micro_solve,
+    generic assembly), Legendre inputs and a fit whose solves truncate."""
+    from bsde_solver._backend import DeviceInputs
+    from bsde_solver._lib import BASIS_LEGENDRE, BASIS_POLY
+    from bsde_solver.core.calculus.basis import LegendreBasis
+
+    rng = np.random.RandomState(77)
+    for d, p, ranks, N, kind, target in ((6, 4, [1, 4, 4, 4, 4, 4, 1], 40000, "poly", "log"), (4, 5, [1, 3, 5, 3, 1], 2048, "poly", "log"),
+                                         (5, 3, [1, 2, 3, 3, 2, 1], 1531, "leg", "log"), (12, 4, [1] + [4] * 11 + [1], 70001, "poly", "log"),
+                                         (6, 4, [1, 4, 4, 4, 4, 4, 1], 1 << 13, "poly", "square"), (3, 6, [1, 5, 5, 1], 3000, "poly", "log")):
+        if target == "square":      # the converging fit of test_truncated_solves_inside_a_converging_fit: its solves truncate
+            x = np.tile([1.0, 0.5], d // 2) * np.exp(-0.03 + 0.4 * rng.randn(N, d))
+            y = (x**2).sum(axis=1)
+        else:
+            x = rng.randn(N, d) * 0.7
+            y = np.log(0.5 + 0.5 * (x**2).sum(axis=1)) + 0.1 * x[:, 0]
+        init = flat([rng.rand(ranks[i], p, ranks[i + 1]) * 2 - 1 for i in range(d)])
+        inp = DeviceInputs(BASIS_POLY if kind == "poly" else BASIS_LEGENDRE, p, backend.to_device(np.ascontiguousarray(x.T)),
+                           coef=None if kind == "poly" else LegendreBasis(p)._coef())
+        yd = backend.to_device(y)
+        out, edges = {}, {}
+        try:
+            for key, (pdl, use_graph) in {"pdl": (1, 1), "plain": (0, 1), "eager": (0, 0)}.items():
+                backend.set_option("pdl", pdl)
+                backend.set_option("use_graph", use_graph)
+                got = init.copy()
+                info = backend.fit_als(inp, yd, 6, np.array(ranks, dtype=np.int32), 0, got)
+                out[key] = (got, [int(v) for v in info[:3]])
+                edges[key] = (int(backend.get_stat("graph_edges")), int(backend.get_stat("graph_pdl_edges")))
+        finally:
+            backend.set_option("pdl", 1)
+            backend.set_option("use_graph", 1)
+        assert np.all(np.isfinite(out["eager"][0]))
+        for key in ("pdl", "plain"):
+            assert np.array_equal(out[key][0], out["eager"][0]), (d, p, kind, target, key)
+            assert out[key][1] == out["eager"][1], (d, p, kind, target, key)
+        if target == "square":
+            assert out["pdl"][1][1] > 10, out["pdl"][1]      # this fit converges: many of its solves truncate
+        # with the option the kernel -> kernel edges of the captured sweep are programmatic, without it none is
+        assert edges["pdl"][1] > 0 and edges["plain"] == (edges["pdl"][0], 0), edges
+        if p == 4 and max(ranks) == 4:                       # a chain of 3 kernels per micro-step, every edge programmatic
+            assert edges["pdl"] == (3 * 2 * (d - 1) - 1, 3 * 2 * (d - 1) - 1), edges
+
+
 def test_fast_solve_kernel_matches_the_general_one(backend):
     """k_micro_solve_fast (register-resident Cholesky, n <= 64) against k_micro_solve alone on the same fits: even and odd
     numbers of unknowns, ragged ranks, and agreement with the numpy oracle."""
