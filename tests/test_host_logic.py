@@ -158,3 +158,29 @@ def test_starting_points_of_the_path_simulation():
     x0, n = _x0_row(X0[:, ::1])
     assert x0.shape == (4, 3) and n == 4
     np.testing.assert_array_equal(x0, X0)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line with the base contract's keys, the true sample
+    count of the bounded CPU run in its config, no GPU work — and under a launcher every rank but 0 exits without output."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+    other = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), timeout=300)
+    assert other.returncode == 0 and other.stdout.strip() == "", other.stdout[-500:] + other.stderr[-500:]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, res.stdout[-2000:]
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"].startswith("samples*sweeps/s") and j["unit"] == "samples*sweeps/s"
+    assert j["higher_is_better"] is True and j["gpu_launches"] == 0 and j["steps"] == 1 and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    n = j["config"]["samples_per_gpu"]
+    assert n < (1 << 20) and f"N=2^{n.bit_length() - 1} samples" in j["config"]["workload"]      # the label says what was run
